@@ -1,0 +1,190 @@
+/* tfrpn.h -- C ABI of libtfrpn_cuda.so: the B200 (sm_100a) box hot path of FurkanOM/tf-rpn.
+ *
+ * The reference has no FFI: its hot path is plain Python over TensorFlow eager ops.  Each
+ * entry point below replaces one reference function (cited file:line, relative to the
+ * reference root) and is what a ctypes binding inside the reference's own modules would
+ * call.  Conventions:
+ *   - all tensors float32 (or int32 where stated), row-major, contiguous, 16-byte aligned;
+ *     a box is [y1, x1, y2, x2], normalised to [0,1];
+ *   - pointers are DEVICE pointers unless the name ends in _host;
+ *   - every function returns 0 (TFRPN_OK) or a negative tfrpn_status; the message is in
+ *     the thread-local tfrpn_last_error();
+ *   - work is enqueued on the caller's stream (0 = legacy default stream); no hidden
+ *     device synchronisation except in the *_host entry points, which return after the
+ *     results are in the caller's host buffers;
+ *   - the caller owns every buffer; the library owns only the per-handle workspace;
+ *   - there is no CPU fallback: without a CUDA device every call fails with TFRPN_ERR_CUDA.
+ */
+#ifndef TFRPN_H_
+#define TFRPN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TFRPN_API __attribute__((visibility("default")))
+#else
+#define TFRPN_API
+#endif
+
+#define TFRPN_VERSION 100 /* 0.1.0 */
+#define TFRPN_MAX_BASE_ANCHORS 64
+#define TFRPN_MAX_SORT_K 11264 /* largest per-image top-k / NMS candidate count the in-SM sort holds (300 outputs) */
+
+typedef enum {
+    TFRPN_OK = 0,
+    TFRPN_ERR_BAD_ARG = -1,     /* null pointer, bad shape, bad config value        */
+    TFRPN_ERR_MISALIGNED = -2,  /* a box pointer is not 16-byte aligned              */
+    TFRPN_ERR_CUDA = -3,        /* CUDA runtime error (text in tfrpn_last_error)     */
+    TFRPN_ERR_WORKSPACE = -4,   /* workspace must grow but the stream is capturing   */
+    TFRPN_ERR_UNSUPPORTED = -5  /* valid request outside what this build implements  */
+} tfrpn_status;
+
+typedef void* tfrpn_stream;            /* a cudaStream_t */
+typedef struct tfrpn_ctx* tfrpn_handle; /* per-device workspace + staging; one thread at a time */
+
+/* ---- hyper_params dict, utils/train_utils.py:5-38 --------------------------------- */
+typedef struct {
+    int32_t img_h, img_w;  /* img_size (reference: one int for both)                    */
+    int32_t fm_h, fm_w;    /* feature_map_shape (reference: one int for both)           */
+    int32_t n_scales, n_ratios;
+    double scales[8];      /* anchor_scales, pixels                                      */
+    double ratios[8];      /* anchor_ratios (Python floats = doubles)                    */
+} tfrpn_anchor_cfg;
+
+typedef struct {
+    float pos_iou_threshold; /* 0.7f  utils/train_utils.py:114 */
+    float neg_iou_threshold; /* 0.3f  utils/train_utils.py:128 */
+    int32_t total_pos;       /* total_pos_bboxes */
+    int32_t total_neg;       /* total_neg_bboxes */
+    float variances[4];      /* [0.1,0.1,0.2,0.2]; deltas are DIVIDED by these (:139) */
+    uint64_t seed;           /* counter-RNG key                                          */
+    uint64_t offset;         /* counter-RNG offset (bump per step; resume = same value)  */
+    int32_t image_offset;    /* global index of image 0 of this shard (multi-GPU)        */
+    int32_t reserved;
+} tfrpn_target_cfg;
+
+/* optional intermediates of target assignment; any pointer may be NULL */
+typedef struct {
+    int32_t* argmax_row;  /* (B,N)  per-anchor best GT   utils/train_utils.py:108 */
+    int32_t* argmax_col;  /* (B,G)  per-GT best anchor   utils/train_utils.py:110 */
+    float* max_iou;       /* (B,N)                       utils/train_utils.py:112 */
+    uint8_t* pos_pre;     /* (B,N)  positives before sampling   (:114-122)       */
+    uint8_t* neg_pre;     /* (B,N)  negative candidates         (:128)           */
+    int32_t* pos_count;   /* (B,)                                (:125)           */
+    int32_t* neg_count;   /* (B,)                                                 */
+} tfrpn_target_debug;
+
+typedef struct {
+    int32_t max_output_size_per_class;
+    int32_t max_total_size;
+    float iou_threshold;   /* suppress iff IoU > thr (strict)                */
+    float score_threshold; /* candidates need score > thr; -INFINITY = all  */
+    int32_t pad_per_class; /* TF flag; output rows = pad ? min(total, per_class) : total */
+    int32_t clip_boxes;    /* clip OUTPUT boxes to [0,1]                     */
+} tfrpn_nms_cfg;
+
+typedef struct {
+    float variances[4];   /* deltas are MULTIPLIED by these, predictor.py:55 */
+    int32_t pre_nms_topn; /* k of tf.nn.top_k, predictor.py:58 (BASELINE: 6000) */
+    int32_t post_nms_topn;/* test_nms_topn = 300, utils/train_utils.py:29   */
+    float nms_iou_threshold; /* 0.7 */
+    int32_t clip;         /* clip decoded boxes to [0,1] before NMS (north star) */
+} tfrpn_proposal_cfg;
+
+/* ---- library ---------------------------------------------------------------------- */
+TFRPN_API int tfrpn_version(void);
+TFRPN_API const char* tfrpn_last_error(void);
+TFRPN_API int tfrpn_create(tfrpn_handle* out, int device /* -1 = current */);
+TFRPN_API int tfrpn_destroy(tfrpn_handle h);
+/* Pre-size the workspace (needed before CUDA-graph capture; otherwise it grows lazily). */
+TFRPN_API int tfrpn_reserve(tfrpn_handle h, int B, int N, int G, int k);
+TFRPN_API size_t tfrpn_workspace_bytes(int B, int N, int G, int k);
+/* number of kernels launched by this library on the calling thread since process start */
+TFRPN_API uint64_t tfrpn_launch_count(void);
+
+/* ---- anchors: utils/bbox_utils.py:3-21 and :23-46 ---------------------------------- */
+TFRPN_API int tfrpn_base_anchors_host(const tfrpn_anchor_cfg* cfg, float* out_host /* (A,4) */);
+TFRPN_API int tfrpn_anchors(const tfrpn_anchor_cfg* cfg, float* out /* (fm_h*fm_w*A,4) */, tfrpn_stream s);
+
+/* ---- generate_iou_map: utils/bbox_utils.py:126-150 --------------------------------- */
+TFRPN_API int tfrpn_iou_map(const float* boxes /* (N,4) or (B,N,4) */, int boxes_batched,
+                  const float* gt_boxes /* (B,G,4) */, int B, int N, int G,
+                  float* out /* (B,N,G) */, tfrpn_stream s);
+
+/* ---- get_deltas_from_bboxes: utils/bbox_utils.py:98-124 (no variance scaling) ------ */
+TFRPN_API int tfrpn_encode_deltas(const float* boxes /* (N,4) or (B,N,4) */, int boxes_batched,
+                        const float* gt_boxes /* (B,N,4) */, int B, int N,
+                        float* out /* (B,N,4) */, tfrpn_stream s);
+
+/* ---- get_bboxes_from_deltas: utils/bbox_utils.py:72-96; optionally the caller's
+ *      `deltas *= variances` (predictor.py:55) and the clip of the proposal pipeline --- */
+TFRPN_API int tfrpn_decode(const float* anchors /* (N,4) or (B,N,4) */, int anchors_batched,
+                 const float* deltas /* (B,N,4) */, const float* variances_host_or_null /* [4] */,
+                 int clip, int B, int N, float* out /* (B,N,4) */, tfrpn_stream s);
+
+/* ---- normalize_bboxes / denormalize_bboxes: utils/bbox_utils.py:152-182 ------------ */
+TFRPN_API int tfrpn_scale_boxes(const float* boxes, int64_t n_boxes, float height, float width,
+                      int denormalize /* 0: divide; 1: multiply then round-half-even */,
+                      float* out, tfrpn_stream s);
+
+/* ---- calculate_rpn_actual_outputs: utils/train_utils.py:84-144 --------------------- */
+TFRPN_API int tfrpn_rpn_targets(tfrpn_handle h, const float* anchors /* (N,4) */,
+                      const float* gt_boxes /* (B,G,4) */, const int32_t* gt_labels /* (B,G) */,
+                      int B, int N, int G, const tfrpn_target_cfg* cfg,
+                      float* deltas /* (B,N,4) */, float* labels /* (B,N) == (B,F,F,A) */,
+                      const tfrpn_target_debug* dbg_or_null, tfrpn_stream s);
+
+/* ---- randomly_select_xyz_mask: utils/train_utils.py:50-65 (counter RNG) ------------ */
+TFRPN_API int tfrpn_select_mask(tfrpn_handle h, const uint8_t* mask /* (B,N) 0/1 */,
+                      const int32_t* select /* (n_select,) device; n_select = 1 or B */,
+                      int n_select, int B, int N, uint64_t seed, uint64_t offset,
+                      int rng_stream /* 0 = positives word, 1 = negatives word */,
+                      int image_offset, uint8_t* out /* (B,N) */, tfrpn_stream s);
+
+/* ---- tf.nn.top_k + tf.gather(batch_dims=1): predictor.py:58-60 --------------------- */
+TFRPN_API int tfrpn_topk(tfrpn_handle h, const float* scores /* (B,N) */, int B, int N, int k,
+               float* values /* (B,k) */, int32_t* indices /* (B,k) */,
+               const float* boxes_or_null /* (N,4) or (B,N,4) */, int boxes_batched,
+               float* gathered_or_null /* (B,k,4) */, tfrpn_stream s);
+
+/* ---- non_max_suppression: utils/bbox_utils.py:48-70 (1 class, q = 1) ---------------
+ * rows = cfg->pad_per_class ? min(max_total_size, per_class) : max_total_size          */
+TFRPN_API int tfrpn_nms(tfrpn_handle h, const float* boxes /* (B,K,4) */, const float* scores /* (B,K) */,
+              int B, int K, const tfrpn_nms_cfg* cfg,
+              float* out_boxes /* (B,rows,4) */, float* out_scores /* (B,rows) */,
+              float* out_classes /* (B,rows), zeros */, int32_t* valid /* (B,) */,
+              int32_t* keep_idx_or_null /* (B,rows), -1 padded */, tfrpn_stream s);
+
+/* ---- composed proposal stage: predictor.py:52-60 -> clip ->
+ *      bbox_utils.py:48-70 with k = pre_nms_topn, 300 @ 0.7 ---------------------------- */
+TFRPN_API int tfrpn_proposals(tfrpn_handle h, const float* rpn_reg /* (B,N,4) == (B,F,F,4A) */,
+                    const float* rpn_cls /* (B,N) == (B,F,F,A) */, const float* anchors /* (N,4) */,
+                    int B, int N, const tfrpn_proposal_cfg* cfg,
+                    float* out_boxes /* (B,post,4) */, float* out_scores /* (B,post) */,
+                    int32_t* valid /* (B,) */, int32_t* keep_idx_or_null /* (B,post) */,
+                    tfrpn_stream s);
+
+/* ---- host-buffer entry points (what a NumPy / tf.numpy() caller binds): pinned staging,
+ *      H2D, kernels, D2H, stream sync -- all inside the call ---------------------------- */
+TFRPN_API int tfrpn_rpn_targets_host(tfrpn_handle h, const float* anchors_dev /* (N,4) device */,
+                           const float* gt_boxes_host, const int32_t* gt_labels_host,
+                           int B, int N, int G, const tfrpn_target_cfg* cfg,
+                           float* deltas_host, float* labels_host, tfrpn_stream s);
+TFRPN_API int tfrpn_proposals_host(tfrpn_handle h, const float* rpn_reg_host, const float* rpn_cls_host,
+                         const float* anchors_dev /* (N,4) device */, int B, int N,
+                         const tfrpn_proposal_cfg* cfg, float* out_boxes_host,
+                         float* out_scores_host, int32_t* valid_host, int32_t* keep_idx_host_or_null,
+                         tfrpn_stream s);
+/* page-locked host memory for the caller's batches (so H2D/D2H run at full PCIe rate) */
+TFRPN_API int tfrpn_host_alloc(void** out, size_t bytes);
+TFRPN_API int tfrpn_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFRPN_H_ */

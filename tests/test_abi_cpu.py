@@ -1,0 +1,84 @@
+"""CPU-side checks of the boundary: the shared library loads, exports exactly the symbols that
+include/tfrpn.h declares, and refuses to run without a CUDA device (no fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "tfrpn.h")).read()
+    return sorted(set(re.findall(r"^TFRPN_API [\w \*]+?\b(tfrpn_\w+)\(", text, flags=re.M)))
+
+
+def test_header_symbols_are_bound_and_exported():
+    from tfrpn import _lib
+    syms = header_symbols()
+    assert len(syms) >= 20
+    assert sorted(_lib.PROTOTYPES) == syms
+    lib = _lib.load()
+    for s in syms:
+        assert hasattr(lib, s), s
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (tfrpn_\w+)", nm)))
+    assert exported == syms
+
+
+def test_version_and_error_string():
+    from tfrpn import _lib
+    lib = _lib.load()
+    assert lib.tfrpn_version() == 100
+    assert isinstance(lib.tfrpn_last_error(), bytes)
+
+
+def test_base_anchors_host_matches_oracle():
+    """The only host-side arithmetic in the library (utils/bbox_utils.py:3-21)."""
+    import numpy as np
+    from oracle import rpn_oracle as O
+    from tfrpn import _lib
+    from tfrpn.utils import bbox_utils
+    for hp in (O.get_hyper_params("vgg16"), O.get_hyper_params("mobilenet_v2"),
+               dict(O.get_hyper_params("vgg16"), img_size=(800, 1333), feature_map_shape=(50, 84))):
+        cfg = bbox_utils._anchor_cfg(hp)
+        host = (C.c_float * 36)()
+        assert _lib.load().tfrpn_base_anchors_host(C.byref(cfg), host) == 0
+        got = np.asarray(list(host), np.float32).reshape(9, 4)
+        assert np.array_equal(got.view(np.uint32), O.generate_base_anchors(hp).view(np.uint32))
+
+
+def test_bad_arguments_are_reported():
+    from tfrpn import _lib
+    lib = _lib.load()
+    assert lib.tfrpn_base_anchors_host(None, None) == -1
+    assert b"null" in lib.tfrpn_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(lib.tfrpn_iou_map(None, 0, None, 1, 1, 1, None, None))
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tfrpn import _lib
+    from tfrpn.utils import bbox_utils, train_utils
+    out = C.c_void_p()
+    assert _lib.load().tfrpn_create(C.byref(out), -1) == -3      # TFRPN_ERR_CUDA
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bbox_utils.generate_anchors(train_utils.get_hyper_params("vgg16"))
+    import numpy as np
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bbox_utils.generate_iou_map(np.zeros((4, 4), np.float32), np.zeros((1, 2, 4), np.float32))
+
+
+def test_hyper_params_quirks_match_reference():
+    """utils/train_utils.py:20-38: only existing keys with truthy values are overridden."""
+    from tfrpn.utils import train_utils
+    hp = dict(train_utils.get_hyper_params("vgg16", total_pos_bboxes=64, bogus=3, total_neg_bboxes=0))
+    assert hp["total_pos_bboxes"] == 64 and "bogus" not in hp and hp["total_neg_bboxes"] == 128
+    assert hp["anchor_count"] == 9 and hp["test_nms_topn"] == 300
+    train_utils.get_hyper_params("vgg16", total_pos_bboxes=128)
+    assert train_utils.get_step_size(10, 4) == 3

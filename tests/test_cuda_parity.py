@@ -1,0 +1,457 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in Python functions) against
+the oracle on the same seeded inputs and against the committed golden vectors.
+
+Bars (BASELINE.json north star): integer / index / label / mask outputs bit-exact; IoU (IEEE-exact
+ops only) bit-exact; deltas and decoded boxes (exp / log) within 1e-6 relative in fp32.
+"""
+import numpy as np
+import pytest
+
+from oracle import rpn_oracle as O
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+RTOL = 1e-6  # the tolerance BASELINE.json's north_star states for floating point
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a, F32), np.ascontiguousarray(b, F32)
+    return a.shape == b.shape and bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
+def close(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and bool(np.all(np.abs(a - b) <= RTOL * np.maximum(1.0, np.abs(b))))
+
+
+@pytest.fixture(scope="module")
+def T(cuda_device):
+    import torch
+    import tfrpn
+    from tfrpn.utils import bbox_utils, train_utils
+
+    class Ns:
+        pass
+    ns = Ns()
+    ns.torch, ns.bbox, ns.train, ns.tfrpn, ns.dev = torch, bbox_utils, train_utils, tfrpn, cuda_device
+    ns.cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    ns.np = lambda t: t.detach().cpu().numpy()
+    return ns
+
+
+HP_C4 = dict(O.get_hyper_params("vgg16"), img_size=(800, 1333), feature_map_shape=(50, 84))
+
+
+# ---------------------------------------------------------------- anchors
+@pytest.mark.parametrize("hp", [O.get_hyper_params("vgg16"), O.get_hyper_params("mobilenet_v2"), HP_C4,
+                                dict(O.get_hyper_params("vgg16"), feature_map_shape=7, anchor_scales=[64, 300],
+                                     anchor_ratios=[1., 3., 0.25, 0.7])],
+                         ids=["vgg16", "mobilenet_v2", "c4_1333x800", "odd"])
+def test_anchors_bit_exact(T, hp):
+    hp = dict(hp, anchor_count=len(hp["anchor_ratios"]) * len(hp["anchor_scales"]))
+    assert bits_equal(T.np(T.bbox.generate_anchors(hp)), O.generate_anchors(hp))
+    assert bits_equal(T.np(T.bbox.generate_base_anchors(hp)), O.generate_base_anchors(hp))
+
+
+def test_anchors_match_golden(T, golden):
+    for bb in ("vgg16", "mobilenet_v2"):
+        assert bits_equal(T.np(T.bbox.generate_anchors(T.train.get_hyper_params(bb))), golden["anchors_" + bb])
+
+
+# ---------------------------------------------------------------- IoU map
+def rand_boxes(rng, *shape):
+    a = np.sort(rng.uniform(0, 1, size=shape + (2, 2)), axis=-2).astype(F32)
+    return np.stack([a[..., 0, 0], a[..., 0, 1], a[..., 1, 0], a[..., 1, 1]], axis=-1)
+
+
+@pytest.mark.parametrize("B,N,G,batched", [(3, 257, 7, True), (3, 257, 7, False), (1, 1, 1, False), (2, 128, 50, True),
+                                           (2, 8649, 50, False), (2, 1000, 300, False), (5, 129, 3, True)])
+def test_iou_map_bit_exact(T, B, N, G, batched):
+    rng = np.random.default_rng(B * 1000 + N + G)
+    boxes = rand_boxes(rng, B, N) if batched else rand_boxes(rng, N)
+    gt = rand_boxes(rng, B, G)
+    gt[0, 0] = 0                                  # padded GT row
+    if N > 5:
+        gt[-1, -1] = boxes[-1, 5] if batched else boxes[5]   # IoU == 1
+    got = T.np(T.bbox.generate_iou_map(T.cu(boxes), T.cu(gt)))
+    assert bits_equal(got, O.generate_iou_map(boxes, gt))
+
+
+def test_iou_map_golden_and_nan(T, golden):
+    got = T.np(T.bbox.generate_iou_map(T.cu(golden["iou_boxes"]), T.cu(golden["iou_gt"])))
+    assert bits_equal(got, golden["iou_map_batched"])
+    got = T.np(T.bbox.generate_iou_map(T.cu(golden["iou_boxes"][0]), T.cu(golden["iou_gt"])))
+    assert bits_equal(got, golden["iou_map_unbatched"])
+    z = np.zeros((1, 2, 4), F32)                   # both degenerate -> 0/0 = NaN, like the reference
+    got = T.np(T.bbox.generate_iou_map(T.cu(z[0]), T.cu(z)))
+    assert np.isnan(got).all() and np.isnan(O.generate_iou_map(z[0], z)).all()
+
+
+def test_iou_map_accepts_numpy_host_buffers(T):
+    rng = np.random.default_rng(5)
+    boxes, gt = rand_boxes(rng, 300), rand_boxes(rng, 2, 9)
+    got = T.bbox.generate_iou_map(boxes, gt)
+    assert isinstance(got, np.ndarray) and bits_equal(got, O.generate_iou_map(boxes, gt))
+
+
+# ---------------------------------------------------------------- encode / decode / scale
+def test_encode_decode_golden(T, golden):
+    enc = T.np(T.bbox.get_deltas_from_bboxes(T.cu(golden["enc_boxes"]), T.cu(golden["enc_gt"])))
+    ref = golden["enc_deltas"]
+    assert close(enc, ref)
+    assert bits_equal(enc[..., :2], ref[..., :2])         # dy, dx use IEEE-exact ops only
+    assert np.array_equal(enc == 0, ref == 0)
+    dec = T.np(T.bbox.get_bboxes_from_deltas(T.cu(golden["iou_boxes"]), T.cu(golden["dec_deltas"])))
+    assert close(dec, golden["dec_boxes_batched"])
+    dec = T.np(T.bbox.get_bboxes_from_deltas(T.cu(golden["iou_boxes"][0]), T.cu(golden["dec_deltas"])))
+    assert close(dec, golden["dec_boxes_unbatched"])
+
+
+def test_encode_decode_kat(T):
+    a = np.asarray([[[0, 0, .5, .5]]], F32)
+    g = np.asarray([[[.25, .25, .75, .75]]], F32)
+    assert np.array_equal(T.np(T.bbox.get_deltas_from_bboxes(T.cu(a), T.cu(g)))[0, 0], np.asarray([.5, .5, 0, 0], F32))
+    assert np.array_equal(T.np(T.bbox.get_deltas_from_bboxes(T.cu(a), T.cu(g * 0)))[0, 0], np.zeros(4, F32))
+    d = (np.asarray([[[5, 5, 0, 0]]], F32) * np.asarray([.1, .1, .2, .2], F32)).astype(F32)
+    assert np.array_equal(T.np(T.bbox.get_bboxes_from_deltas(T.cu(a), T.cu(d))), g)
+    assert np.array_equal(T.np(T.bbox.get_bboxes_from_deltas(T.cu(a), T.cu(d * 0))), a)
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (2, 511), (3, 513), (64, 8649)])
+def test_decode_encode_random_and_roundtrip(T, B, N):
+    rng = np.random.default_rng(N)
+    anchors = rand_boxes(rng, N)
+    deltas = rng.normal(0, 0.5, size=(B, N, 4)).astype(F32)
+    dec = T.np(T.bbox.get_bboxes_from_deltas(T.cu(anchors), T.cu(deltas)))
+    assert close(dec, O.get_bboxes_from_deltas(anchors, deltas))
+    # size-independent property: encode(decode(d)) ~ d wherever the anchor is not degenerate
+    enc = T.np(T.bbox.get_deltas_from_bboxes(T.cu(anchors), T.cu(dec)))
+    ok = ((anchors[:, 2] - anchors[:, 0]) > 1e-2) & ((anchors[:, 3] - anchors[:, 1]) > 1e-2)
+    assert np.allclose(enc[:, ok], deltas[:, ok], atol=2e-3)
+    assert close(enc, O.get_deltas_from_bboxes(anchors, dec))
+
+
+def test_normalize_denormalize_bit_exact(T, golden):
+    assert bits_equal(T.np(T.bbox.normalize_bboxes(T.cu(golden["norm_in"]), 375, 500)), golden["norm_out"])
+    assert bits_equal(T.np(T.bbox.denormalize_bboxes(T.cu(golden["iou_boxes"]), 375, 500)), golden["denorm_out"])
+
+
+# ---------------------------------------------------------------- target assignment
+def check_targets(T, hp, anchors, gtb, gtl, seed, offset, image_offset=0):
+    d, l, dbg = T.train.calculate_rpn_actual_outputs(T.cu(anchors), T.cu(gtb), T.cu(gtl), hp, seed=seed,
+                                                     offset=offset, image_offset=image_offset, return_debug=True)
+    d, l = T.np(d), T.np(l)
+    dbg = {k: T.np(v) for k, v in dbg.items()}
+    od, ol, odbg = O.calculate_rpn_actual_outputs(anchors, gtb, gtl, hp, seed=seed, offset=offset,
+                                                  image_offset=image_offset, return_debug=True)
+    assert np.array_equal(dbg["argmax_row"], odbg["argmax_row"])
+    assert np.array_equal(dbg["argmax_col"], odbg["argmax_col"])
+    assert np.array_equal(dbg["max_iou"], odbg["max_iou"])          # numerically (+-0 compare equal)
+    assert np.array_equal(dbg["pos_pre"].astype(bool), odbg["pos_pre"])
+    assert np.array_equal(dbg["neg_pre"].astype(bool), odbg["neg_pre"])
+    assert np.array_equal(dbg["pos_count"], odbg["pos_count"])
+    assert np.array_equal(dbg["neg_count"], odbg["neg_count"])
+    assert l.shape == ol.shape and bits_equal(l, ol)                  # labels {1,0,-1} bit-exact
+    assert np.array_equal(d != 0, od != 0) and close(d, od)
+    assert bits_equal(d[..., :2], od[..., :2])
+    return d, l, dbg
+
+
+@pytest.mark.parametrize("tag,bb", [("t_vgg16", "vgg16"), ("t_mnv2", "mobilenet_v2"), ("t_smallquota", "vgg16")])
+def test_targets_golden(T, golden, tag, bb):
+    tp, tn = (int(v) for v in golden[tag + "_quota"])
+    hp = dict(O.get_hyper_params(bb, total_pos_bboxes=tp, total_neg_bboxes=tn))
+    seed, offset = (int(v) for v in golden[tag + "_seed_offset"])
+    anchors = golden["anchors_" + bb]
+    d, l, _ = check_targets(T, hp, anchors, golden[tag + "_gt_boxes"], golden[tag + "_gt_labels"], seed, offset)
+    shape = tuple(golden[tag + "_delta_shape"])
+    gd = np.zeros((shape[0] * shape[1], 4), F32)
+    gd[golden[tag + "_delta_rows"]] = golden[tag + "_delta_vals"]
+    assert close(d, gd.reshape(shape))
+    assert bits_equal(l.reshape(shape[0], -1), golden[tag + "_labels"].astype(F32))
+
+
+@pytest.mark.parametrize("cfg,B", [("C1", 1), ("C2", 64), ("C3", 8), ("C4", 2)])
+def test_targets_vs_oracle_synthetic(T, cfg, B):
+    from tfrpn import synthetic
+    bb, _, G, over = synthetic.CONFIGS[cfg]
+    hp = dict(O.get_hyper_params(bb), **over)
+    anchors = O.generate_anchors(hp)
+    rng = np.random.default_rng(1000 * int(cfg[1]))
+    gtb, gtl = synthetic.gt_batch(rng, B, G)
+    d, l, dbg = check_targets(T, hp, anchors, gtb, gtl, seed=2026, offset=3)
+    lab = l.reshape(B, -1)
+    assert np.all((lab == 1).sum(-1) <= hp["total_pos_bboxes"])
+    assert np.all((lab == 1).sum(-1) + (lab == 0).sum(-1) <= hp["total_pos_bboxes"] + hp["total_neg_bboxes"])
+
+
+def test_targets_edge_cases(T):
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors = O.generate_anchors(hp)
+    # all-padding image, G = 1, exact duplicates (ties), tiny GT, one image with 50 valid boxes
+    gtb = np.zeros((4, 1, 4), F32); gtl = np.full((4, 1), -1, np.int32)
+    gtb[1, 0] = anchors[8648]; gtl[1, 0] = 5
+    gtb[2, 0] = [0.4, 0.4, 0.41, 0.41]; gtl[2, 0] = 1
+    gtb[3, 0] = [0, 0, 1, 1]; gtl[3, 0] = 1
+    check_targets(T, hp, anchors, gtb, gtl, seed=1, offset=0)
+    hp2 = dict(hp, total_pos_bboxes=3, total_neg_bboxes=5)
+    rng = np.random.default_rng(3)
+    from tfrpn import synthetic
+    gtb, gtl = synthetic.gt_batch(rng, 3, 50)
+    uniq, inv, counts = np.unique(anchors, axis=0, return_inverse=True, return_counts=True)
+    dup = np.flatnonzero(counts[inv.reshape(-1)] > 1)
+    gtb[0, 0] = anchors[dup[-1]]; gtl[0, 0] = 2     # tie group at IoU 1: lowest index must win
+    check_targets(T, hp2, anchors, gtb, gtl, seed=77, offset=12345678901)
+
+
+def test_targets_sharded_equals_unsharded(T):
+    """shard r of R must equal rows [r*B/R, (r+1)*B/R) of the unsharded run bit for bit."""
+    from tfrpn import synthetic
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors = T.bbox.generate_anchors(hp)
+    gtb, gtl = synthetic.gt_batch(np.random.default_rng(9), 8, 20)
+    full_d, full_l = T.train.calculate_rpn_actual_outputs(anchors, T.cu(gtb), T.cu(gtl), hp, seed=4, offset=1)
+    for r in range(4):
+        sl = slice(2 * r, 2 * r + 2)
+        d, l = T.train.calculate_rpn_actual_outputs(anchors, T.cu(gtb[sl]), T.cu(gtl[sl]), hp, seed=4, offset=1,
+                                                    image_offset=2 * r)
+        assert T.torch.equal(d, full_d[sl]) and T.torch.equal(l, full_l[sl])
+
+
+def test_targets_sampling_changes_with_offset_only(T):
+    from tfrpn import synthetic
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors = T.bbox.generate_anchors(hp)
+    gtb, gtl = synthetic.gt_batch(np.random.default_rng(10), 2, 30)
+    a = T.train.calculate_rpn_actual_outputs(anchors, T.cu(gtb), T.cu(gtl), hp, seed=1, offset=5)
+    b = T.train.calculate_rpn_actual_outputs(anchors, T.cu(gtb), T.cu(gtl), hp, seed=1, offset=5)
+    c = T.train.calculate_rpn_actual_outputs(anchors, T.cu(gtb), T.cu(gtl), hp, seed=1, offset=6)
+    assert T.torch.equal(a[1], b[1]) and T.torch.equal(a[0], b[0])
+    assert not T.torch.equal(a[1], c[1])
+
+
+@pytest.mark.parametrize("B,N,quota", [(4, 500, [50]), (4, 8649, [0, 10, 100000, 128]), (2, 70000, [1, 69999])])
+def test_select_mask_bit_exact(T, B, N, quota):
+    rng = np.random.default_rng(N)
+    mask = rng.uniform(size=(B, N)) < 0.3
+    got = T.np(T.train.randomly_select_xyz_mask(T.cu(mask), T.cu(np.asarray(quota, np.int32)), seed=9, offset=2,
+                                                stream=1, image_offset=3))
+    want = O.randomly_select_xyz_mask(mask, quota, seed=9, offset=2, stream=1, image_offset=3)
+    assert got.dtype == bool and np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------- top-k
+@pytest.mark.parametrize("B,N,k", [(2, 8649, 10), (3, 8649, 6000), (2, 9216, 9216), (1, 37, 1), (2, 100000, 6000),
+                                   (1, 500000, 6000), (2, 5000, 4999)])
+def test_topk_bit_exact(T, B, N, k):
+    rng = np.random.default_rng(N + k)
+    scores = rng.uniform(0, 1, size=(B, N)).astype(F32)
+    boxes = rand_boxes(rng, B, N)
+    v, i, g = T.bbox.top_k_boxes(T.cu(scores), k, T.cu(boxes))
+    ov, oi = O.top_k(scores, k)
+    assert np.array_equal(T.np(i), oi) and bits_equal(T.np(v), ov)
+    assert bits_equal(T.np(g), np.take_along_axis(boxes, oi[..., None].astype(np.int64), axis=1))
+
+
+def test_topk_ties_and_negative_scores(T):
+    rng = np.random.default_rng(0)
+    scores = rng.integers(-3, 4, size=(3, 4000)).astype(F32) / F32(4)      # massive ties, +-0
+    scores[0, :10] = -0.0
+    v, i = T.bbox.top_k_boxes(T.cu(scores), 1500)
+    ov, oi = O.top_k(scores, 1500)
+    assert np.array_equal(T.np(i), oi) and np.array_equal(T.np(v), ov)
+    s = np.asarray([[.5, .9, .5, .9, .1, .5]], F32)
+    v, i = T.bbox.top_k_boxes(T.cu(s), 5)
+    assert list(T.np(i)[0]) == [1, 3, 0, 2, 5]
+
+
+def test_topk_golden_predictor_sequence(T, golden):
+    hp = T.train.get_hyper_params("vgg16")
+    anchors = T.bbox.generate_anchors(hp)
+    reg, cls = golden["pred_reg"], golden["pred_cls"]
+    B = reg.shape[0]
+    deltas = T.cu(reg).reshape(B, -1, 4) * T.torch.tensor(hp["variances"], device=T.dev)   # predictor.py:55
+    boxes = T.bbox.get_bboxes_from_deltas(anchors, deltas)
+    _, idx, sel = T.bbox.top_k_boxes(T.cu(cls).reshape(B, -1), 10, boxes)
+    assert np.array_equal(T.np(idx), golden["pred_top10_idx"])
+    assert close(T.np(sel), golden["pred_top10_boxes"])
+    assert close(T.np(boxes)[:, golden["pred_boxes_sample_idx"]], golden["pred_boxes_sample"])
+
+
+# ---------------------------------------------------------------- NMS
+def run_nms(T, boxes, scores, **kw):
+    B, K = scores.shape
+    r = T.bbox.non_max_suppression(T.cu(boxes.reshape(B, K, 1, 4)), T.cu(scores.reshape(B, K, 1)),
+                                   return_indices=True, **kw)
+    return [T.np(x) for x in r]
+
+
+def check_nms(T, boxes, scores, **kw):
+    B, K = scores.shape
+    got = run_nms(T, boxes, scores, **kw)
+    want = O.combined_non_max_suppression(boxes.reshape(B, K, 1, 4), scores.reshape(B, K, 1), return_indices=True,
+                                          **kw)
+    assert np.array_equal(got[3], want[3])                     # valid_detections
+    assert np.array_equal(got[4], want[4])                     # keep list, order included
+    assert bits_equal(got[0], want[0]) and bits_equal(got[1], want[1]) and bits_equal(got[2], want[2])
+    return got
+
+
+def test_nms_golden(T, golden):
+    got = run_nms(T, golden["nms_in_boxes"], golden["nms_in_scores"], max_output_size_per_class=50,
+                  max_total_size=60, iou_threshold=0.3, score_threshold=0.25)
+    assert bits_equal(got[0], golden["nms_out_boxes"]) and bits_equal(got[1], golden["nms_out_scores"])
+    assert bits_equal(got[2], golden["nms_out_classes"]) and np.array_equal(got[3], golden["nms_out_valid"])
+
+
+@pytest.mark.parametrize("K,per_class,total,thr,sthr", [
+    (300, 50, 60, 0.3, 0.25), (6000, 300, 300, 0.7, float("-inf")), (1000, 1000, 1000, 0.5, float("-inf")),
+    (129, 7, 5, 0.1, 0.5), (1, 3, 3, 0.5, float("-inf")), (2500, 300, 300, 0.05, float("-inf")),
+    (700, 10, 10, 0.5, 2.0)])
+def test_nms_vs_oracle(T, K, per_class, total, thr, sthr):
+    from tfrpn import synthetic
+    rng = np.random.default_rng(K)
+    boxes, scores = synthetic.nms_boxes(rng, 3, K, 0.05, 0.4)
+    if K > 10:
+        boxes[0, 3] = boxes[0, 3][[2, 3, 0, 1]]
+        boxes[0, 4] = [0.5, 0.5, 0.5, 0.7]
+        boxes[1, 7] = [-0.2, 0.1, 0.4, 1.3]
+    got = check_nms(T, boxes, scores, max_output_size_per_class=per_class, max_total_size=total,
+                    iou_threshold=thr, score_threshold=sthr)
+    # property: kept boxes are pairwise below the threshold and scores are non-increasing
+    for b in range(3):
+        n = got[3][b]
+        assert np.all(np.diff(got[1][b, :n]) <= 0)
+
+
+def test_nms_heavy_suppression_and_flags(T):
+    rng = np.random.default_rng(1)
+    K = 4000
+    c = rng.uniform(0.45, 0.55, size=(2, K, 2)); s = rng.uniform(0.3, 0.4, size=(2, K, 2))
+    boxes = np.concatenate([c - s / 2, c + s / 2], -1).astype(F32)     # nearly everything overlaps
+    scores = (rng.permutation(2 * K).reshape(2, K).astype(F32) + 1) / F32(2 * K + 2)
+    check_nms(T, boxes, scores, max_output_size_per_class=300, max_total_size=300, iou_threshold=0.7)
+    check_nms(T, boxes, scores, max_output_size_per_class=20, max_total_size=300, iou_threshold=0.7, pad_per_class=True)
+    check_nms(T, boxes * 1.5 - 0.2, scores, max_output_size_per_class=30, max_total_size=30, iou_threshold=0.6,
+              clip_boxes=False)
+
+
+def test_nms_kat_one_ulp_threshold(T):
+    f = F32
+    boxes = np.stack([np.asarray(v, f) for v in ([0, 0, 1, 1], [0, 0, 1, .5], [.2, .2, .2, .8], [1, .5, 0, 0])])[None]
+    scores = np.asarray([[.9, .8, .7, .6]], f)
+    lo, hi = np.nextafter(f(.5), f(0)), np.nextafter(f(.5), f(1))
+    keep = {}
+    for thr in (lo, f(.5), hi):
+        r = run_nms(T, boxes, scores, max_output_size_per_class=10, max_total_size=10, iou_threshold=float(thr))
+        keep[float(thr)] = list(r[4][0, :r[3][0]])
+    assert keep[float(lo)] == [0, 2] and keep[float(f(.5))] == [0, 1, 2] and keep[float(hi)] == [0, 1, 2]
+
+
+def test_nms_equal_scores_lower_index_first(T):
+    rng = np.random.default_rng(2)
+    from tfrpn import synthetic
+    boxes, _ = synthetic.nms_boxes(rng, 2, 500, 0.05, 0.4)
+    scores = (rng.integers(0, 5, size=(2, 500)).astype(F32)) / F32(8)
+    check_nms(T, boxes, scores, max_output_size_per_class=100, max_total_size=100, iou_threshold=0.4)
+
+
+# ---------------------------------------------------------------- composed proposal stage
+def test_proposals_golden(T, golden):
+    hp = T.train.get_hyper_params("vgg16")
+    anchors = T.bbox.generate_anchors(hp)
+    k, post, thr = golden["prop_k_post_thr"]
+    b, s, v, keep = T.tfrpn.generate_proposals(T.cu(golden["pred_reg"]), T.cu(golden["pred_cls"]), anchors, hp,
+                                               pre_nms_topn=int(k), post_nms_topn=int(post),
+                                               nms_iou_threshold=float(thr))
+    assert np.array_equal(T.np(v), golden["prop_valid"])
+    assert bits_equal(T.np(s), golden["prop_scores"])
+    assert close(T.np(b), golden["prop_boxes"])
+
+
+@pytest.mark.parametrize("cfg,B", [("C1", 1), ("C2", 64), ("C3", 4), ("C4", 2)])
+def test_proposals_vs_oracle(T, cfg, B):
+    from tfrpn import synthetic
+    bb, _, _, over = synthetic.CONFIGS[cfg]
+    hp = dict(O.get_hyper_params(bb), **over)
+    fh, fw = O._pair(hp["feature_map_shape"])
+    anchors = O.generate_anchors(hp)
+    rng = np.random.default_rng(7 + int(cfg[1]))
+    reg, cls = synthetic.head_outputs(rng, B, fh, fw, 9)
+    gb, gs, gv, gk = (T.np(x) for x in T.tfrpn.generate_proposals(T.cu(reg), T.cu(cls), T.cu(anchors), hp))
+    # (a) chain parity, bit-exact: the oracle's top-k + NMS applied to the boxes the CUDA decode produced
+    var = np.asarray(hp["variances"], F32)
+    dec = T.np(T.bbox.get_bboxes_from_deltas(T.cu(anchors), T.cu((reg.reshape(B, -1, 4) * var).astype(F32))))
+    dec = np.clip(dec, 0, 1)
+    assert close(dec, np.clip(O.get_bboxes_from_deltas(anchors, reg.reshape(B, -1, 4) * var), 0, 1))
+    sc = cls.reshape(B, -1)
+    k = min(6000, sc.shape[1])
+    ts, ti = O.top_k(sc, k)
+    tb = np.take_along_axis(dec, ti[..., None].astype(np.int64), axis=1)
+    nb, ns, _, nv, ni = O.combined_non_max_suppression(tb.reshape(B, k, 1, 4), ts.reshape(B, k, 1), 300, 300,
+                                                       iou_threshold=0.7, return_indices=True)
+    keep = np.where(ni >= 0, np.take_along_axis(ti, np.maximum(ni, 0).astype(np.int64), axis=1), -1)
+    assert np.array_equal(gv, nv) and np.array_equal(gk, keep)
+    assert bits_equal(gs, ns) and bits_equal(gb, nb)
+    # (b) end to end against the pure oracle: identical keep lists unless a 1-ulp exp difference
+    #     lands exactly on the 0.7 threshold (never observed on these seeds)
+    ob, os_, ov, ok = O.generate_proposals(reg, cls, anchors, hp)
+    assert np.array_equal(gv, ov) and np.array_equal(gk, ok)
+    assert close(gb, ob) and bits_equal(gs, os_)
+
+
+def test_proposals_host_buffers_equal_device_path(T):
+    from tfrpn import synthetic
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors = T.bbox.generate_anchors(hp)
+    reg, cls = synthetic.head_outputs(np.random.default_rng(3), 3, 31, 31, 9)
+    dev = T.tfrpn.generate_proposals(T.cu(reg), T.cu(cls), anchors, hp)
+    host = T.tfrpn.generate_proposals(reg, cls, T.np(anchors), hp)
+    for a, b in zip(dev, host):
+        assert isinstance(b, np.ndarray) and np.array_equal(T.np(a), b)
+
+
+# ---------------------------------------------------------------- boundary behaviour
+def test_rejects_bad_inputs(T):
+    hp = T.train.get_hyper_params("vgg16")
+    anchors = T.bbox.generate_anchors(hp)
+    with pytest.raises(ValueError):
+        T.bbox.generate_iou_map(anchors.double(), T.cu(np.zeros((1, 2, 4), F32)))
+    with pytest.raises(ValueError):
+        T.bbox.get_bboxes_from_deltas(anchors, T.cu(np.zeros((2, 5, 4), F32)))
+    with pytest.raises(ValueError):
+        T.train.calculate_rpn_actual_outputs(anchors[:100], T.cu(np.zeros((1, 2, 4), F32)),
+                                             T.cu(np.zeros((1, 2), np.int32)), hp)
+    with pytest.raises(NotImplementedError):
+        T.bbox.non_max_suppression(T.cu(np.zeros((1, 4, 2, 4), F32)), T.cu(np.zeros((1, 4, 2), F32)),
+                                   max_output_size_per_class=2, max_total_size=2)
+    with pytest.raises(ValueError):
+        T.bbox.top_k_boxes(T.cu(np.zeros((1, 4), F32)), 5)
+
+
+def test_c_abi_host_entry_points(T):
+    """tfrpn_rpn_targets_host / tfrpn_proposals_host: host pointers in, host results out."""
+    import ctypes as C
+    from tfrpn import _lib, synthetic
+    from tfrpn.proposals import proposal_cfg
+    from tfrpn.utils.train_utils import _target_cfg
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors_np = O.generate_anchors(hp)
+    anchors = T.cu(anchors_np)
+    B, G, N = 5, 13, 8649
+    gtb, gtl = synthetic.gt_batch(np.random.default_rng(21), B, G)
+    d = np.empty((B, N, 4), F32); l = np.empty((B, N), F32)
+    lib, h = _lib.load(), _lib.handle(T.dev.index)
+    tc = _target_cfg(hp, 5, 6, 0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(lib.tfrpn_rpn_targets_host(h, anchors.data_ptr(), vp(gtb), vp(gtl), B, N, G, C.byref(tc), vp(d), vp(l), None))
+    od, ol = O.calculate_rpn_actual_outputs(anchors_np, gtb, gtl, hp, seed=5, offset=6)
+    assert bits_equal(l, ol.reshape(B, N)) and close(d, od)
+    reg, cls = synthetic.head_outputs(np.random.default_rng(22), B, 31, 31, 9)
+    pc = proposal_cfg(hp)
+    ob = np.empty((B, 300, 4), F32); os_ = np.empty((B, 300), F32)
+    ov = np.empty((B,), np.int32); ok = np.empty((B, 300), np.int32)
+    _lib.check(lib.tfrpn_proposals_host(h, vp(reg), vp(cls), anchors.data_ptr(), B, N, C.byref(pc), vp(ob), vp(os_),
+                                        vp(ov), vp(ok), None))
+    wb, ws, wv, wk = O.generate_proposals(reg, cls, anchors_np, hp)
+    assert np.array_equal(ov, wv) and np.array_equal(ok, wk) and bits_equal(os_, ws) and close(ob, wb)

@@ -1,0 +1,221 @@
+// api.cu -- handle, error reporting, workspace, and the host-buffer entry points of libtfrpn_cuda.so.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+struct tfrpn_ctx {
+    int device = 0;
+    int sm_count = 148;
+    char* ws = nullptr;       // device workspace (kernels' scratch)
+    size_t ws_bytes = 0;
+    char* dev = nullptr;      // device staging for the *_host entry points
+    size_t dev_bytes = 0;
+    char* pinned = nullptr;   // page-locked host staging
+    size_t pinned_bytes = 0;
+};
+
+namespace tfrpn {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+int fail(int status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(TFRPN_ERR_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+void count_launch() { ++g_launches; }
+
+size_t targets_workspace_bytes(int B, int N, int G);  // targets.cu
+
+int sm_count_of(tfrpn_handle h) { return h ? h->sm_count : 148; }
+
+static int grow(char** buf, size_t* have, size_t want, cudaStream_t s, bool pinned) {
+    if (want <= *have) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+        return fail(TFRPN_ERR_WORKSPACE, "workspace must grow to %zu B while the stream is capturing; call tfrpn_reserve first", want);
+    if (*buf) {
+        TFRPN_CHECK_CUDA(cudaStreamSynchronize(s));
+        TFRPN_CHECK_CUDA(cudaDeviceSynchronize());
+        if (pinned) TFRPN_CHECK_CUDA(cudaFreeHost(*buf)); else TFRPN_CHECK_CUDA(cudaFree(*buf));
+        *buf = nullptr;
+        *have = 0;
+    }
+    want = (want + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+    void* p = nullptr;
+    if (pinned) TFRPN_CHECK_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault)); else TFRPN_CHECK_CUDA(cudaMalloc(&p, want));
+    *buf = static_cast<char*>(p);
+    *have = want;
+    return 0;
+}
+
+int ensure_workspace(tfrpn_handle h, size_t bytes, cudaStream_t s, char** out) {
+    if (int rc = grow(&h->ws, &h->ws_bytes, bytes, s, false)) return rc;
+    *out = h->ws;
+    return 0;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace tfrpn
+
+using namespace tfrpn;
+
+extern "C" int tfrpn_version(void) { return TFRPN_VERSION; }
+extern "C" const char* tfrpn_last_error(void) { return g_err; }
+extern "C" uint64_t tfrpn_launch_count(void) { return g_launches; }
+
+extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
+    if (!out) return fail(TFRPN_ERR_BAD_ARG, "create: out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(TFRPN_ERR_CUDA, "no CUDA device available (%s); libtfrpn_cuda has no CPU fallback",
+                    e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    if (device < 0) TFRPN_CHECK_CUDA(cudaGetDevice(&device));
+    if (device >= count) return fail(TFRPN_ERR_BAD_ARG, "create: device %d of %d", device, count);
+    TFRPN_CHECK_CUDA(cudaSetDevice(device));
+    tfrpn_ctx* h = new tfrpn_ctx();
+    h->device = device;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = h;
+    return 0;
+}
+
+extern "C" int tfrpn_destroy(tfrpn_handle h) {
+    if (!h) return 0;
+    if (h->ws) cudaFree(h->ws);
+    if (h->dev) cudaFree(h->dev);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    delete h;
+    return 0;
+}
+
+extern "C" size_t tfrpn_workspace_bytes(int B, int N, int G, int k) {
+    (void)k;  // top-k / NMS work entirely in shared memory
+    if (B <= 0 || N <= 0) return 0;
+    return targets_workspace_bytes(B, N, G > 0 ? G : 1);
+}
+
+extern "C" int tfrpn_reserve(tfrpn_handle h, int B, int N, int G, int k) {
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "reserve: null handle");
+    char* ws;
+    return ensure_workspace(h, tfrpn_workspace_bytes(B, N, G, k), nullptr, &ws);
+}
+
+extern "C" int tfrpn_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail(TFRPN_ERR_BAD_ARG, "host_alloc: out is null");
+    TFRPN_CHECK_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+extern "C" int tfrpn_host_free(void* p) {
+    if (p) TFRPN_CHECK_CUDA(cudaFreeHost(p));
+    return 0;
+}
+
+// copy from a caller's host buffer: directly when it is page-locked, else through pinned staging
+static int h2d(tfrpn_handle h, void* dst, const void* src, size_t bytes, char** pin_cursor, cudaStream_t s) {
+    cudaPointerAttributes attr;
+    bool is_pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!is_pinned) {
+        memcpy(*pin_cursor, src, bytes);
+        src = *pin_cursor;
+        *pin_cursor += align256(bytes);
+    }
+    (void)h;
+    TFRPN_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+extern "C" int tfrpn_rpn_targets_host(tfrpn_handle h, const float* anchors_dev, const float* gt_boxes_host,
+                                      const int32_t* gt_labels_host, int B, int N, int G, const tfrpn_target_cfg* cfg,
+                                      float* deltas_host, float* labels_host, tfrpn_stream s) {
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: null handle");
+    if (!gt_boxes_host || !gt_labels_host || !deltas_host || !labels_host)
+        return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: null pointer");
+    if (B <= 0 || N <= 0 || G <= 0) return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: bad shape");
+    cudaStream_t st = as_stream(s);
+    const size_t b_gt = align256((size_t)B * G * 16), b_gl = align256((size_t)B * G * 4);
+    const size_t b_d = align256((size_t)B * N * 16), b_l = align256((size_t)B * N * 4);
+    if (int rc = grow(&h->dev, &h->dev_bytes, b_gt + b_gl + b_d + b_l, st, false)) return rc;
+    if (int rc = grow(&h->pinned, &h->pinned_bytes, b_gt + b_gl + b_d + b_l, st, true)) return rc;
+    char* d = h->dev;
+    float* d_gt = reinterpret_cast<float*>(d);
+    int32_t* d_gl = reinterpret_cast<int32_t*>(d + b_gt);
+    float* d_d = reinterpret_cast<float*>(d + b_gt + b_gl);
+    float* d_l = reinterpret_cast<float*>(d + b_gt + b_gl + b_d);
+    char* pin = h->pinned;
+    if (int rc = h2d(h, d_gt, gt_boxes_host, (size_t)B * G * 16, &pin, st)) return rc;
+    if (int rc = h2d(h, d_gl, gt_labels_host, (size_t)B * G * 4, &pin, st)) return rc;
+    if (int rc = tfrpn_rpn_targets(h, anchors_dev, d_gt, d_gl, B, N, G, cfg, d_d, d_l, nullptr, s)) return rc;
+    // results: straight into the caller's buffers when they are page-locked, else via staging
+    cudaPointerAttributes attr;
+    bool out_pinned = cudaPointerGetAttributes(&attr, deltas_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                      cudaPointerGetAttributes(&attr, labels_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (out_pinned) {
+        TFRPN_CHECK_CUDA(cudaMemcpyAsync(deltas_host, d_d, (size_t)B * N * 16, cudaMemcpyDeviceToHost, st));
+        TFRPN_CHECK_CUDA(cudaMemcpyAsync(labels_host, d_l, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+        TFRPN_CHECK_CUDA(cudaStreamSynchronize(st));
+    } else {
+        char* p_d = h->pinned + b_gt + b_gl;
+        char* p_l = p_d + b_d;
+        TFRPN_CHECK_CUDA(cudaMemcpyAsync(p_d, d_d, (size_t)B * N * 16, cudaMemcpyDeviceToHost, st));
+        TFRPN_CHECK_CUDA(cudaMemcpyAsync(p_l, d_l, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+        TFRPN_CHECK_CUDA(cudaStreamSynchronize(st));
+        memcpy(deltas_host, p_d, (size_t)B * N * 16);
+        memcpy(labels_host, p_l, (size_t)B * N * 4);
+    }
+    return 0;
+}
+
+extern "C" int tfrpn_proposals_host(tfrpn_handle h, const float* rpn_reg_host, const float* rpn_cls_host,
+                                    const float* anchors_dev, int B, int N, const tfrpn_proposal_cfg* cfg,
+                                    float* out_boxes_host, float* out_scores_host, int32_t* valid_host,
+                                    int32_t* keep_idx_host_or_null, tfrpn_stream s) {
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "proposals_host: null handle");
+    if (!rpn_reg_host || !rpn_cls_host || !cfg || !out_boxes_host || !out_scores_host || !valid_host)
+        return fail(TFRPN_ERR_BAD_ARG, "proposals_host: null pointer");
+    if (B <= 0 || N <= 0 || cfg->post_nms_topn <= 0) return fail(TFRPN_ERR_BAD_ARG, "proposals_host: bad shape");
+    cudaStream_t st = as_stream(s);
+    const int P = cfg->post_nms_topn;
+    const size_t b_reg = align256((size_t)B * N * 16), b_cls = align256((size_t)B * N * 4);
+    const size_t b_ob = align256((size_t)B * P * 16), b_os = align256((size_t)B * P * 4);
+    const size_t b_v = align256((size_t)B * 4), b_k = align256((size_t)B * P * 4);
+    const size_t total = b_reg + b_cls + b_ob + b_os + b_v + b_k;
+    if (int rc = grow(&h->dev, &h->dev_bytes, total, st, false)) return rc;
+    if (int rc = grow(&h->pinned, &h->pinned_bytes, total, st, true)) return rc;
+    char* d = h->dev;
+    float* d_reg = reinterpret_cast<float*>(d);
+    float* d_cls = reinterpret_cast<float*>(d + b_reg);
+    char* d_out = d + b_reg + b_cls;  // boxes | scores | valid | keep, contiguous
+    float* d_ob = reinterpret_cast<float*>(d_out);
+    float* d_os = reinterpret_cast<float*>(d_out + b_ob);
+    int32_t* d_v = reinterpret_cast<int32_t*>(d_out + b_ob + b_os);
+    int32_t* d_k = reinterpret_cast<int32_t*>(d_out + b_ob + b_os + b_v);
+    char* pin = h->pinned;
+    if (int rc = h2d(h, d_reg, rpn_reg_host, (size_t)B * N * 16, &pin, st)) return rc;
+    if (int rc = h2d(h, d_cls, rpn_cls_host, (size_t)B * N * 4, &pin, st)) return rc;
+    if (int rc = tfrpn_proposals(h, d_reg, d_cls, anchors_dev, B, N, cfg, d_ob, d_os, d_v, d_k, s)) return rc;
+    // the four small results come back in ONE D2H copy through pinned staging
+    char* p_out = h->pinned + b_reg + b_cls;
+    const size_t out_bytes = b_ob + b_os + b_v + b_k;
+    TFRPN_CHECK_CUDA(cudaMemcpyAsync(p_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    TFRPN_CHECK_CUDA(cudaStreamSynchronize(st));
+    memcpy(out_boxes_host, p_out, (size_t)B * P * 16);
+    memcpy(out_scores_host, p_out + b_ob, (size_t)B * P * 4);
+    memcpy(valid_host, p_out + b_ob + b_os, (size_t)B * 4);
+    if (keep_idx_host_or_null) memcpy(keep_idx_host_or_null, p_out + b_ob + b_os + b_v, (size_t)B * P * 4);
+    return 0;
+}

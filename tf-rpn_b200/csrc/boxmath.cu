@@ -1,0 +1,299 @@
+// boxmath.cu -- anchors, IoU map, delta encode / decode, (de)normalise.
+// Replaces utils/bbox_utils.py:3-46, :72-96, :98-124, :126-150, :152-182 of the reference.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace tfrpn {
+
+// ------------------------------------------------------------------------------------------------
+// K0 anchors (utils/bbox_utils.py:23-46).  One thread per anchor; the grid coordinate is evaluated
+// in float64 exactly like `tf.range(0,F)/F + stride/2` (int32 truediv -> f64) and rounded once.
+// ------------------------------------------------------------------------------------------------
+struct BaseAnchors {
+    float4 box[TFRPN_MAX_BASE_ANCHORS];
+};
+
+__global__ void __launch_bounds__(256) anchors_kernel(BaseAnchors base, int A, int fm_h, int fm_w,
+                                                      double half_stride_y, double half_stride_x,
+                                                      float4* __restrict__ out) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    int N = fm_h * fm_w * A;
+    if (n >= N) return;
+    int c = n / A, a = n - c * A;
+    int i = c / fm_w, j = c - i * fm_w;
+    float y = __double2float_rn(__dadd_rn(__ddiv_rn((double)i, (double)fm_h), half_stride_y));
+    float x = __double2float_rn(__dadd_rn(__ddiv_rn((double)j, (double)fm_w), half_stride_x));
+    float4 b = base.box[a];
+    float4 o = make_float4(__fadd_rn(b.x, y), __fadd_rn(b.y, x), __fadd_rn(b.z, y), __fadd_rn(b.w, x));
+    out[n] = clip01(o);
+}
+
+static int check_anchor_cfg(const tfrpn_anchor_cfg* cfg) {
+    if (!cfg) return fail(TFRPN_ERR_BAD_ARG, "anchor cfg is null");
+    if (cfg->img_h <= 0 || cfg->img_w <= 0 || cfg->fm_h <= 0 || cfg->fm_w <= 0)
+        return fail(TFRPN_ERR_BAD_ARG, "img_size / feature_map_shape must be positive");
+    if (cfg->n_scales <= 0 || cfg->n_scales > 8 || cfg->n_ratios <= 0 || cfg->n_ratios > 8)
+        return fail(TFRPN_ERR_BAD_ARG, "1..8 anchor scales and ratios supported");
+    return 0;
+}
+
+// utils/bbox_utils.py:3-21 on the host, same dtype walk: the quotient scale^2/ratio is a double,
+// rounded to f32, then f32 sqrt; h = w * f32(ratio); halves are exact.
+static int base_anchors_host(const tfrpn_anchor_cfg* cfg, float* out) {
+    int a = 0;
+    for (int s = 0; s < cfg->n_scales; ++s) {
+        double sw = cfg->scales[s] / (double)cfg->img_w;
+        double sh = cfg->scales[s] / (double)cfg->img_h;
+        for (int r = 0; r < cfg->n_ratios; ++r, ++a) {
+            double ratio = cfg->ratios[r];
+            float w = sqrtf((float)(pow(sw, 2.0) / ratio));
+            float h = sqrtf((float)(pow(sh, 2.0) / ratio)) * (float)ratio;
+            out[a * 4 + 0] = -h / 2.0f;
+            out[a * 4 + 1] = -w / 2.0f;
+            out[a * 4 + 2] = h / 2.0f;
+            out[a * 4 + 3] = w / 2.0f;
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 generate_iou_map (utils/bbox_utils.py:126-150), materialised (B,N,G).  HBM-write bound:
+// 4*B*N*G bytes out.  One CTA owns TILE_N boxes of one image; boxes+areas and the image's GT
+// boxes+areas are staged in shared memory; threads walk the CONTIGUOUS output tile so every warp
+// store is one full 128-byte line.  (n,g) advance incrementally -- no integer division per element.
+// ------------------------------------------------------------------------------------------------
+constexpr int IOU_THREADS = 256;
+constexpr int IOU_TILE_N = 128;
+
+__global__ void __launch_bounds__(IOU_THREADS) iou_map_kernel(const float4* __restrict__ boxes,
+                                                              long long box_batch_stride,
+                                                              const float4* __restrict__ gt, int N, int G,
+                                                              float* __restrict__ out) {
+    extern __shared__ float4 smem4[];
+    float4* sbox = smem4;                      // [IOU_TILE_N]
+    float4* sgt = smem4 + IOU_TILE_N;          // [G]
+    float* sbarea = reinterpret_cast<float*>(sgt + G);  // [IOU_TILE_N]
+    float* sgarea = sbarea + IOU_TILE_N;       // [G]
+
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * IOU_TILE_N;
+    const int tn = min(IOU_TILE_N, N - n0);
+    const float4* bx = boxes + (long long)b * box_batch_stride + n0;
+    for (int i = threadIdx.x; i < tn; i += IOU_THREADS) {
+        float4 v = ldg_f4(bx + i);
+        sbox[i] = v;
+        sbarea[i] = box_area(v);
+    }
+    const float4* gb = gt + (long long)b * G;
+    for (int g = threadIdx.x; g < G; g += IOU_THREADS) {
+        float4 v = ldg_f4(gb + g);
+        sgt[g] = v;
+        sgarea[g] = box_area(v);
+    }
+    __syncthreads();
+
+    float* o = out + ((long long)b * N + n0) * G;
+    const int total = tn * G;
+    const int dn = IOU_THREADS / G, dg = IOU_THREADS - dn * G;
+    int e = threadIdx.x;
+    int n = e / G, g = e - n * G;
+#pragma unroll 4
+    for (; e < total; e += IOU_THREADS) {
+        float v = iou_ref(sbox[n], sbarea[n], sgt[g], sgarea[g]);
+        stg_f1_stream(o + e, v);
+        n += dn;
+        g += dg;
+        if (g >= G) { g -= G; n += 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Elementwise kernels: one float4 box per element.  grid = (ceil(N / (256*2)), B): blockIdx.y is the
+// image, so the (N,4) broadcast operand is indexed without a modulo; each thread keeps two
+// independent 128-bit loads per operand in flight.
+// ------------------------------------------------------------------------------------------------
+constexpr int EW_THREADS = 256;
+constexpr int EW_PER_THREAD = 2;
+
+// get_deltas_from_bboxes (utils/bbox_utils.py:98-124)
+__global__ void __launch_bounds__(EW_THREADS) encode_kernel(const float4* __restrict__ boxes, int boxes_batched,
+                                                            const float4* __restrict__ gt, int N,
+                                                            float4* __restrict__ out) {
+    const long long img = (long long)blockIdx.y * N;
+    const float4* bx = boxes + (boxes_batched ? img : 0);
+    const int n0 = blockIdx.x * (EW_THREADS * EW_PER_THREAD) + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < EW_PER_THREAD; ++u) {
+        int n = n0 + u * EW_THREADS;
+        if (n < N) {
+            float4 b = boxes_batched ? ldg_f4_stream(bx + n) : ldg_f4(bx + n);
+            float4 g = ldg_f4_stream(gt + img + n);
+            stg_f4_stream(out + img + n, encode_ref(b, g));
+        }
+    }
+}
+
+// get_bboxes_from_deltas (utils/bbox_utils.py:72-96) with the caller-side `deltas *= variances`
+// (predictor.py:55) and the proposal pipeline's clip fused in.  K3: 32*B*N algorithmic bytes.
+template <bool SCALE, bool CLIP>
+__global__ void __launch_bounds__(EW_THREADS) decode_kernel(const float4* __restrict__ anchors, int anchors_batched,
+                                                            const float4* __restrict__ deltas, float4 var, int N,
+                                                            float4* __restrict__ out) {
+    const long long img = (long long)blockIdx.y * N;
+    const float4* an = anchors + (anchors_batched ? img : 0);
+    const int n0 = blockIdx.x * (EW_THREADS * EW_PER_THREAD) + threadIdx.x;
+    float4 d[EW_PER_THREAD], a[EW_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < EW_PER_THREAD; ++u) {
+        int n = n0 + u * EW_THREADS;
+        if (n < N) {
+            d[u] = ldg_f4_stream(deltas + img + n);
+            a[u] = anchors_batched ? ldg_f4_stream(an + n) : ldg_f4(an + n);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_PER_THREAD; ++u) {
+        int n = n0 + u * EW_THREADS;
+        if (n < N) {
+            float4 dd = SCALE ? mul4(d[u], var) : d[u];
+            float4 o = decode_ref(a[u], dd);
+            if (CLIP) o = clip01(o);
+            stg_f4_stream(out + img + n, o);
+        }
+    }
+}
+
+// normalize_bboxes / denormalize_bboxes (utils/bbox_utils.py:152-182)
+__global__ void __launch_bounds__(EW_THREADS) scale_boxes_kernel(const float4* __restrict__ in, long long total,
+                                                                 float h, float w, int denorm,
+                                                                 float4* __restrict__ out) {
+    long long stride = (long long)gridDim.x * EW_THREADS;
+    for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += stride) {
+        float4 b = ldg_f4_stream(in + i), o;
+        if (denorm) {
+            o = make_float4(rintf(__fmul_rn(b.x, h)), rintf(__fmul_rn(b.y, w)), rintf(__fmul_rn(b.z, h)),
+                            rintf(__fmul_rn(b.w, w)));
+        } else {
+            o = make_float4(__fdiv_rn(b.x, h), __fdiv_rn(b.y, w), __fdiv_rn(b.z, h), __fdiv_rn(b.w, w));
+        }
+        stg_f4_stream(out + i, o);
+    }
+}
+
+static int ew_grid(long long total, int per_thread) {
+    long long blocks = (total + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    return (int)blocks;
+}
+static dim3 ew_grid2(int B, int N) {
+    return dim3((N + EW_THREADS * EW_PER_THREAD - 1) / (EW_THREADS * EW_PER_THREAD), B);
+}
+
+}  // namespace tfrpn
+
+using namespace tfrpn;
+
+extern "C" int tfrpn_base_anchors_host(const tfrpn_anchor_cfg* cfg, float* out_host) {
+    if (int rc = check_anchor_cfg(cfg)) return rc;
+    if (!out_host) return fail(TFRPN_ERR_BAD_ARG, "out_host is null");
+    return base_anchors_host(cfg, out_host);
+}
+
+extern "C" int tfrpn_anchors(const tfrpn_anchor_cfg* cfg, float* out, tfrpn_stream s) {
+    if (int rc = check_anchor_cfg(cfg)) return rc;
+    if (!out) return fail(TFRPN_ERR_BAD_ARG, "out is null");
+    if (!aligned16(out)) return fail(TFRPN_ERR_MISALIGNED, "anchors output must be 16-byte aligned");
+    BaseAnchors base;
+    float tmp[TFRPN_MAX_BASE_ANCHORS * 4];
+    base_anchors_host(cfg, tmp);
+    int A = cfg->n_scales * cfg->n_ratios;
+    for (int a = 0; a < A; ++a) base.box[a] = make_float4(tmp[4 * a], tmp[4 * a + 1], tmp[4 * a + 2], tmp[4 * a + 3]);
+    long long N = (long long)cfg->fm_h * cfg->fm_w * A;
+    if (N > (1LL << 30)) return fail(TFRPN_ERR_BAD_ARG, "too many anchors");
+    double hy = (1.0 / cfg->fm_h) / 2, hx = (1.0 / cfg->fm_w) / 2;
+    int blocks = (int)((N + 255) / 256);
+    anchors_kernel<<<blocks, 256, 0, as_stream(s)>>>(base, A, cfg->fm_h, cfg->fm_w, hy, hx,
+                                                     reinterpret_cast<float4*>(out));
+    TFRPN_AFTER_LAUNCH("anchors_kernel");
+    return 0;
+}
+
+extern "C" int tfrpn_iou_map(const float* boxes, int boxes_batched, const float* gt_boxes, int B, int N, int G,
+                             float* out, tfrpn_stream s) {
+    if (!boxes || !gt_boxes || !out) return fail(TFRPN_ERR_BAD_ARG, "iou_map: null pointer");
+    if (B < 0 || N < 0 || G < 0) return fail(TFRPN_ERR_BAD_ARG, "iou_map: negative shape");
+    if (B == 0 || N == 0 || G == 0) return 0;
+    if (B > 65535) return fail(TFRPN_ERR_UNSUPPORTED, "iou_map: B > 65535");
+    if (!aligned16(boxes) || !aligned16(gt_boxes)) return fail(TFRPN_ERR_MISALIGNED, "iou_map: boxes must be 16-byte aligned");
+    size_t smem = (size_t)(IOU_TILE_N + G) * (sizeof(float4) + sizeof(float));
+    if (smem > 200 * 1024) return fail(TFRPN_ERR_UNSUPPORTED, "iou_map: G=%d too large for shared memory", G);
+    static thread_local bool attr_set = false;
+    if (smem > 48 * 1024 && !attr_set) {
+        TFRPN_CHECK_CUDA(cudaFuncSetAttribute(iou_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((N + IOU_TILE_N - 1) / IOU_TILE_N, B);
+    iou_map_kernel<<<grid, IOU_THREADS, smem, as_stream(s)>>>(
+        reinterpret_cast<const float4*>(boxes), boxes_batched ? (long long)N : 0LL,
+        reinterpret_cast<const float4*>(gt_boxes), N, G, out);
+    TFRPN_AFTER_LAUNCH("iou_map_kernel");
+    return 0;
+}
+
+extern "C" int tfrpn_encode_deltas(const float* boxes, int boxes_batched, const float* gt_boxes, int B, int N,
+                                   float* out, tfrpn_stream s) {
+    if (!boxes || !gt_boxes || !out) return fail(TFRPN_ERR_BAD_ARG, "encode: null pointer");
+    if (B < 0 || N < 0) return fail(TFRPN_ERR_BAD_ARG, "encode: negative shape");
+    long long total = (long long)B * N;
+    if (total == 0) return 0;
+    if (!aligned16(boxes) || !aligned16(gt_boxes) || !aligned16(out))
+        return fail(TFRPN_ERR_MISALIGNED, "encode: pointers must be 16-byte aligned");
+    if (B > 65535) return fail(TFRPN_ERR_UNSUPPORTED, "encode: B > 65535");
+    encode_kernel<<<ew_grid2(B, N), EW_THREADS, 0, as_stream(s)>>>(
+        reinterpret_cast<const float4*>(boxes), boxes_batched, reinterpret_cast<const float4*>(gt_boxes), N,
+        reinterpret_cast<float4*>(out));
+    TFRPN_AFTER_LAUNCH("encode_kernel");
+    return 0;
+}
+
+extern "C" int tfrpn_decode(const float* anchors, int anchors_batched, const float* deltas,
+                            const float* variances_host_or_null, int clip, int B, int N, float* out,
+                            tfrpn_stream s) {
+    if (!anchors || !deltas || !out) return fail(TFRPN_ERR_BAD_ARG, "decode: null pointer");
+    if (B < 0 || N < 0) return fail(TFRPN_ERR_BAD_ARG, "decode: negative shape");
+    long long total = (long long)B * N;
+    if (total == 0) return 0;
+    if (!aligned16(anchors) || !aligned16(deltas) || !aligned16(out))
+        return fail(TFRPN_ERR_MISALIGNED, "decode: pointers must be 16-byte aligned");
+    float4 var = make_float4(1.f, 1.f, 1.f, 1.f);
+    const bool scale = variances_host_or_null != nullptr;
+    if (scale) var = make_float4(variances_host_or_null[0], variances_host_or_null[1], variances_host_or_null[2],
+                                 variances_host_or_null[3]);
+    const float4* a4 = reinterpret_cast<const float4*>(anchors);
+    const float4* d4 = reinterpret_cast<const float4*>(deltas);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    if (B > 65535) return fail(TFRPN_ERR_UNSUPPORTED, "decode: B > 65535");
+    dim3 grid = ew_grid2(B, N);
+    cudaStream_t st = as_stream(s);
+    if (scale && clip) decode_kernel<true, true><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);
+    else if (scale) decode_kernel<true, false><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);
+    else if (clip) decode_kernel<false, true><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);
+    else decode_kernel<false, false><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);
+    TFRPN_AFTER_LAUNCH("decode_kernel");
+    return 0;
+}
+
+extern "C" int tfrpn_scale_boxes(const float* boxes, int64_t n_boxes, float height, float width, int denormalize,
+                                 float* out, tfrpn_stream s) {
+    if (!boxes || !out) return fail(TFRPN_ERR_BAD_ARG, "scale_boxes: null pointer");
+    if (n_boxes < 0) return fail(TFRPN_ERR_BAD_ARG, "scale_boxes: negative count");
+    if (n_boxes == 0) return 0;
+    if (!aligned16(boxes) || !aligned16(out)) return fail(TFRPN_ERR_MISALIGNED, "scale_boxes: 16-byte alignment");
+    scale_boxes_kernel<<<ew_grid(n_boxes, 1), EW_THREADS, 0, as_stream(s)>>>(
+        reinterpret_cast<const float4*>(boxes), n_boxes, height, width, denormalize, reinterpret_cast<float4*>(out));
+    TFRPN_AFTER_LAUNCH("scale_boxes_kernel");
+    return 0;
+}
