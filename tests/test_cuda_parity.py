@@ -168,7 +168,7 @@ def test_targets_golden(T, golden, tag, bb):
     gd = np.zeros((shape[0] * shape[1], 4), F32)
     gd[golden[tag + "_delta_rows"]] = golden[tag + "_delta_vals"]
     assert close(d, gd.reshape(shape))
-    assert bits_equal(l.reshape(shape[0], -1), golden[tag + "_labels"].astype(F32))
+    assert bits_equal(l.reshape(shape[0], -1), golden[tag + "_labels"].astype(F32).reshape(shape[0], -1))
 
 
 @pytest.mark.parametrize("cfg,B", [("C1", 1), ("C2", 64), ("C3", 8), ("C4", 2)])
