@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- RPN target + proposal images/sec on B200 (BASELINE.json's metric and config C2).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+A "step" is one pass of the hot path over one synthetic batch: calculate_rpn_actual_outputs
+(target assignment) + generate_proposals (decode, clip, top-6000, NMS 300 @ 0.7) for B = 64
+VGG16-RPN 500x500 images per GPU.  `value` = images/s with inputs resident in HBM (device timed,
+CUDA events, max over ranks); `e2e` = the same through the host-buffer C-ABI entry points with the
+H2D / D2H copies inside the timed region.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tf-rpn_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "rpn_target+proposal_images_per_sec"
+WORKLOAD = ("C2: VGG16-RPN 500x500 (31x31x9 = 8649 anchors), batch 64 per GPU, <=50 GT boxes/image, "
+            "pre-NMS top-6000 / post-NMS 300 @ IoU 0.7")
+B_PER_GPU, G_MAX, PRE_NMS, SETS = 64, 50, 6000, 12
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_inputs(rank, n_sets, B):
+    """SURVEY 8d synthetic inputs; seed = 1000*config + rank.  Two generated sets, the rest are
+    batch-rolled copies (distinct memory is what matters for the L2 rotation)."""
+    from tfrpn import synthetic
+    rng = np.random.default_rng(1000 * 2 + rank)
+    base = []
+    for _ in range(2):
+        gtb, gtl = synthetic.gt_batch(rng, B, G_MAX)
+        reg, cls = synthetic.head_outputs(rng, B, 31, 31, 9)
+        base.append((gtb, gtl, reg, cls))
+    sets = []
+    for s in range(n_sets):
+        gtb, gtl, reg, cls = base[s % 2]
+        sh = s // 2
+        sets.append(tuple(np.ascontiguousarray(np.roll(a, sh, axis=0)) for a in (gtb, gtl, reg, cls)))
+    return sets
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz, self.stop_flag = [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def sample(self):
+        nv = self.nv
+        if nv is None:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for name in ("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap", "HwPowerBrakeSlowdown"):
+                bit = getattr(nv, "nvmlClocksEventReason" + name, getattr(nv, "nvmlClocksThrottleReason" + name, 0))
+                if bit and (r & bit):
+                    self.reasons.add(name)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.002)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1)
+        self.sample()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_path(sets, anchors_np, hp, threads, n_images):
+    """The CPU restatement of one step on `n_images` images (C oracle, OpenMP over images; NumPy
+    oracle if the C library is missing).  Returns (seconds, kind-description)."""
+    from oracle import c_oracle, rpn_oracle
+    gtb, gtl, reg, cls = (a[:n_images] for a in sets[0])
+    t0 = time.perf_counter()
+    if c_oracle.available():
+        c_oracle.rpn_targets(anchors_np, gtb, gtl, hp, seed=1, offset=0, threads=threads)
+        c_oracle.proposals(reg.reshape(n_images, -1, 4), cls.reshape(n_images, -1), anchors_np, hp, PRE_NMS,
+                           threads=threads)
+        what = "oracle/rpn_oracle.c (gcc -O2, OpenMP over images)"
+    else:
+        rpn_oracle.calculate_rpn_actual_outputs(anchors_np, gtb, gtl, hp, seed=1)
+        rpn_oracle.generate_proposals(reg, cls, anchors_np, hp, pre_nms_topn=PRE_NMS)
+        what = "oracle/rpn_oracle.py (NumPy, 1 thread)"
+    return time.perf_counter() - t0, what
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm on the host cores.  The reference itself (TF 2.0
+    eager Python) cannot be installed in this image, so this arm times the oracle port with every
+    host thread it can use (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle, rpn_oracle
+    hp = rpn_oracle.get_hyper_params("vgg16")
+    anchors = rpn_oracle.generate_anchors(hp)
+    cores = os.cpu_count() or 1
+    threads = c_oracle.max_threads() if c_oracle.available() else 1
+    sets = make_inputs(0, 2, B_PER_GPU)
+    W, K = max(args.warmup, 1), max(args.steps, 1)
+    K = min(K, 20)   # bounded: each step is a full 64-image batch on the CPU
+    for _ in range(W):
+        cpu_path(sets, anchors, hp, threads, B_PER_GPU)
+    t = 0.0
+    what = ""
+    for _ in range(K):
+        dt, what = cpu_path(sets, anchors, hp, threads, B_PER_GPU)
+        t += dt
+    value = B_PER_GPU * K / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * t / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "note": "CPU arm runs one 64-image batch per step on rank 0"},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": "%d steps x 64 images, %s; host has %d cores" % (K, what, cores)},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tfrpn import _lib
+    from tfrpn.proposals import proposal_cfg
+    from tfrpn.utils import bbox_utils, train_utils
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; tfrpn has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    h = _lib.handle(local)
+
+    hp = dict(train_utils.get_hyper_params("vgg16"))
+    B, G, N, P = B_PER_GPU, G_MAX, 8649, hp["test_nms_topn"]
+    anchors = bbox_utils.generate_anchors(hp)
+    np_sets = make_inputs(rank, SETS, B)
+    cu = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    sets = []
+    for gtb, gtl, reg, cls in np_sets:
+        sets.append(dict(gtb=cu(gtb), gtl=cu(gtl), reg=cu(reg), cls=cu(cls),
+                         deltas=torch.empty((B, N, 4), device=dev), labels=torch.empty((B, N), device=dev),
+                         pb=torch.empty((B, P, 4), device=dev), ps=torch.empty((B, P), device=dev),
+                         pv=torch.empty((B,), dtype=torch.int32, device=dev),
+                         pk=torch.empty((B, P), dtype=torch.int32, device=dev)))
+    set_bytes = sum(t.numel() * t.element_size() for t in sets[0].values())
+    _lib.check(lib.tfrpn_reserve(h, B, N, G, PRE_NMS))
+    pcfg = proposal_cfg(hp, pre_nms_topn=PRE_NMS)
+    side = torch.cuda.Stream(dev)
+
+    def tcfg(step):
+        return train_utils._target_cfg(hp, 2026, step, rank * B)
+
+    def targets(s, step, stream):
+        _lib.check(lib.tfrpn_rpn_targets(h, anchors.data_ptr(), s["gtb"].data_ptr(), s["gtl"].data_ptr(), B, N, G,
+                                         C.byref(tcfg(step)), s["deltas"].data_ptr(), s["labels"].data_ptr(), None,
+                                         stream.cuda_stream))
+
+    def proposals(s, stream):
+        _lib.check(lib.tfrpn_proposals(h, s["reg"].data_ptr(), s["cls"].data_ptr(), anchors.data_ptr(), B, N,
+                                       C.byref(pcfg), s["pb"].data_ptr(), s["ps"].data_ptr(), s["pv"].data_ptr(),
+                                       s["pk"].data_ptr(), stream.cuda_stream))
+
+    def step_eager(i):
+        """targets on the current stream, proposals concurrently on a side stream (independent halves)."""
+        cur = torch.cuda.current_stream(dev)
+        s = sets[i % SETS]
+        side.wait_stream(cur)
+        targets(s, i, cur)
+        proposals(s, side)
+        cur.wait_stream(side)
+
+    # eager warm-up (also sets kernel attributes before any capture)
+    n0 = _lib.launch_count()
+    step_eager(0)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - n0
+
+    graphs = None
+    if not args.no_graph:
+        graphs = []
+        for i in range(SETS):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step_eager(i)
+            graphs.append(g)
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % SETS].replay()
+        else:
+            step_eager(i)
+
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    for i in range(W):
+        run_step(i)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record()
+    for i in range(K):
+        run_step(W + i)
+    e1.record()
+    barrier()
+    clocks = sampler.result()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- p50 single-step latency (device time per step, synchronised between steps) -------------
+    lat = []
+    for i in range(min(K, 200)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run_step(i)
+        b.record()
+        torch.cuda.synchronize()
+        lat.append(a.elapsed_time(b))
+    p50 = float(np.median(lat))
+
+    # ---- per-kernel device time, live (library tracing hooks, eager launches, rotating sets) ----
+    hbm_peak, peak_src = peaks()
+    _lib.check(lib.tfrpn_profile_enable(h, 1))
+    n_prof = 4 * SETS
+    for i in range(n_prof):
+        step_eager(i)
+    kern = {}
+    for kid in range(4):
+        tot, n = C.c_double(), C.c_int()
+        _lib.check(lib.tfrpn_profile_read(h, kid, C.byref(tot), C.byref(n)))
+        if n.value:
+            kern[lib.tfrpn_kernel_name(kid).decode()] = 1e3 * tot.value / n.value   # us per launch
+    _lib.check(lib.tfrpn_profile_enable(h, 0))
+    # algorithmic bytes per launch (DESIGN.md "Kernels"): what each kernel must read and write once
+    alg = {"rpn_iou_argmax_kernel": 16 * N + 16 * B * G + 8 * B * N,
+           "rpn_label_encode_kernel": 8 * B * N + 20 * B * N + 20 * B * G,
+           "proposal_kernel": 4 * B * N + 16 * B * PRE_NMS + 24 * B * P}
+    dominant = max(kern, key=kern.get)
+    dom_us = kern[dominant]
+    achieved = alg[dominant] / (dom_us * 1e-6) / 1e9
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "us_per_launch": dom_us,
+                "algorithmic_bytes": alg[dominant], "peak_source": peak_src}
+    kernels = [{"kernel": k, "us_per_launch": v, "algorithmic_bytes": alg[k],
+                "achieved_gbs": alg[k] / (v * 1e-6) / 1e9, "frac_hbm": alg[k] / (v * 1e-6) / 1e9 / hbm_peak}
+               for k, v in kern.items()]
+    # the IoU/argmax kernel is FP32-ALU bound (B*N*G pairs x ~22 lane-instr), say so
+    if "rpn_iou_argmax_kernel" in kern:
+        alu_peak = 148 * 128 * 1.965e9
+        pairs = B * N * G
+        kernels.append({"kernel": "rpn_iou_argmax_kernel", "bound": "fp32-alu", "pairs": pairs,
+                        "achieved_lane_instr_per_s": pairs * 22 / (kern["rpn_iou_argmax_kernel"] * 1e-6),
+                        "peak_lane_instr_per_s": alu_peak,
+                        "frac_alu": pairs * 22 / (kern["rpn_iou_argmax_kernel"] * 1e-6) / alu_peak})
+
+    # ---- the two HBM-bound drop-in kernels (materialised IoU map K1, decode K3), timed alone ----
+    def timed_loop(fn, reps):
+        for r in range(3):
+            fn(r)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for r in range(reps):
+            fn(r)
+        b.record()
+        torch.cuda.synchronize()
+        return 1e3 * a.elapsed_time(b) / reps   # us per launch
+
+    cur = torch.cuda.current_stream(dev).cuda_stream
+    iou_out = [torch.empty((B, N, G), device=dev) for _ in range(3)]        # 3 x 110.7 MB > L2
+    us = timed_loop(lambda r: _lib.check(lib.tfrpn_iou_map(anchors.data_ptr(), 0, sets[r % SETS]["gtb"].data_ptr(), B, N, G,
+                                                           iou_out[r % 3].data_ptr(), cur)), 30)
+    by = 4 * B * N * G + 16 * (N + B * G)
+    kernels.append({"kernel": "iou_map_kernel", "us_per_launch": us, "algorithmic_bytes": by,
+                    "achieved_gbs": by / (us * 1e-6) / 1e9, "frac_hbm": by / (us * 1e-6) / 1e9 / hbm_peak})
+    del iou_out
+    var = (C.c_float * 4)(*hp["variances"])
+    us = timed_loop(lambda r: _lib.check(lib.tfrpn_decode(anchors.data_ptr(), 0, sets[r % SETS]["reg"].data_ptr(), var, 1, B, N,
+                                                          sets[r % SETS]["deltas"].data_ptr(), cur)), 10 * SETS)
+    by = 32 * B * N + 16 * N
+    kernels.append({"kernel": "decode_kernel", "us_per_launch": us, "algorithmic_bytes": by,
+                    "achieved_gbs": by / (us * 1e-6) / 1e9, "frac_hbm": by / (us * 1e-6) / 1e9 / hbm_peak})
+
+    # ---- e2e: host buffers through the C-ABI host entry points, copies inside the timed region ----
+    def pinned(shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _lib.check(lib.tfrpn_host_alloc(C.byref(p), n))
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    hsets = []
+    for gtb, gtl, reg, cls in np_sets[:2]:
+        d = dict(gtb=pinned(gtb.shape, np.float32), gtl=pinned(gtl.shape, np.int32), reg=pinned(reg.shape, np.float32),
+                 cls=pinned(cls.shape, np.float32), deltas=pinned((B, N, 4), np.float32),
+                 labels=pinned((B, N), np.float32), pb=pinned((B, P, 4), np.float32), ps=pinned((B, P), np.float32),
+                 pv=pinned((B,), np.int32), pk=pinned((B, P), np.int32))
+        d["gtb"][...] = gtb; d["gtl"][...] = gtl; d["reg"][...] = reg; d["cls"][...] = cls
+        hsets.append(d)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def e2e_step(i):
+        s = hsets[i % 2]
+        _lib.check(lib.tfrpn_rpn_targets_host(h, anchors.data_ptr(), vp(s["gtb"]), vp(s["gtl"]), B, N, G,
+                                              C.byref(tcfg(i)), vp(s["deltas"]), vp(s["labels"]), st))
+        _lib.check(lib.tfrpn_proposals_host(h, vp(s["reg"]), vp(s["cls"]), anchors.data_ptr(), B, N, C.byref(pcfg),
+                                            vp(s["pb"]), vp(s["ps"]), vp(s["pv"]), vp(s["pk"]), st))
+
+    Ke = min(K, 200)
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    h2d = B * G * 16 + B * G * 4 + B * N * 16 + B * N * 4
+    d2h = B * N * 16 + B * N * 4 + B * P * 16 + B * P * 4 + B * 4 + B * P * 4
+    e2e = {"value": world * B * Ke / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": Ke, "ms_per_step": 1e3 * t_e2e / Ke,
+           "api": "tfrpn_rpn_targets_host + tfrpn_proposals_host (pinned host buffers in and out)"}
+
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "images sharded, no collective",
+                       "l2": "rotating %d input/output sets (%.0f MB) > 126 MB L2" % (SETS, SETS * set_bytes / 1e6),
+                       "launch": "eager" if graphs is None else "one CUDA graph per set; targets || proposals on two streams"},
+            "p50_ms": p50, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * K),
+            "roofline": roofline, "kernels": kernels}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle, rpn_oracle
+        threads = c_oracle.max_threads() if c_oracle.available() else 1
+        a_np = rpn_oracle.generate_anchors(hp)
+        t_cpu, n_img, what = 0.0, 0, ""
+        while t_cpu < 10.0 and n_img < 64 * 50:
+            dt, what = cpu_path(np_sets, a_np, hp, threads, B)
+            t_cpu += dt
+            n_img += B
+        line["cpu_baseline"] = {"value": n_img / t_cpu, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": "%d images (batches of 64) in %.1f s, %s; host has %d cores"
+                                          % (n_img, t_cpu, what, os.cpu_count() or 1)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -107,6 +107,15 @@ TFRPN_API size_t tfrpn_workspace_bytes(int B, int N, int G, int k);
 /* number of kernels launched by this library on the calling thread since process start */
 TFRPN_API uint64_t tfrpn_launch_count(void);
 
+/* ---- tracing (the reference has none): when enabled, every kernel launched through
+ *      this handle is bracketed by CUDA events on its stream.  Not usable during graph capture. */
+enum { TFRPN_K_IOU_ARGMAX = 0, TFRPN_K_LABEL_ENCODE = 1, TFRPN_K_SELECT_MASK = 2, TFRPN_K_PROPOSAL = 3,
+       TFRPN_K_COUNT = 4 };
+TFRPN_API int tfrpn_profile_enable(tfrpn_handle h, int on);
+/* synchronises, then returns the summed device time and launch count of one kernel id and clears them */
+TFRPN_API int tfrpn_profile_read(tfrpn_handle h, int kernel_id, double* total_ms, int* launches);
+TFRPN_API const char* tfrpn_kernel_name(int kernel_id);
+
 /* ---- anchors: utils/bbox_utils.py:3-21 and :23-46 ---------------------------------- */
 TFRPN_API int tfrpn_base_anchors_host(const tfrpn_anchor_cfg* cfg, float* out_host /* (A,4) */);
 TFRPN_API int tfrpn_anchors(const tfrpn_anchor_cfg* cfg, float* out /* (fm_h*fm_w*A,4) */, tfrpn_stream s);

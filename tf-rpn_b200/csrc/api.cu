@@ -3,6 +3,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 struct tfrpn_ctx {
@@ -14,6 +16,9 @@ struct tfrpn_ctx {
     size_t dev_bytes = 0;
     char* pinned = nullptr;   // page-locked host staging
     size_t pinned_bytes = 0;
+    bool prof_on = false;
+    struct Rec { cudaEvent_t a, b; int id; };
+    std::vector<Rec> recs;
 };
 
 namespace tfrpn {
@@ -65,6 +70,20 @@ int ensure_workspace(tfrpn_handle h, size_t bytes, cudaStream_t s, char** out) {
     return 0;
 }
 
+void prof_begin(tfrpn_handle h, int kernel_id, cudaStream_t s) {
+    if (!h || !h->prof_on) return;
+    tfrpn_ctx::Rec r;
+    r.id = kernel_id;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    h->recs.push_back(r);
+}
+void prof_end(tfrpn_handle h, cudaStream_t s) {
+    if (!h || !h->prof_on || h->recs.empty()) return;
+    cudaEventRecord(h->recs.back().b, s);
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace tfrpn
@@ -74,6 +93,42 @@ using namespace tfrpn;
 extern "C" int tfrpn_version(void) { return TFRPN_VERSION; }
 extern "C" const char* tfrpn_last_error(void) { return g_err; }
 extern "C" uint64_t tfrpn_launch_count(void) { return g_launches; }
+
+extern "C" int tfrpn_profile_enable(tfrpn_handle h, int on) {
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "profile_enable: null handle");
+    h->prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int tfrpn_profile_read(tfrpn_handle h, int kernel_id, double* total_ms, int* launches) {
+    if (!h || !total_ms || !launches) return fail(TFRPN_ERR_BAD_ARG, "profile_read: null pointer");
+    TFRPN_CHECK_CUDA(cudaDeviceSynchronize());
+    double ms = 0;
+    int n = 0;
+    std::vector<tfrpn_ctx::Rec> rest;
+    for (auto& r : h->recs) {
+        if (r.id != kernel_id) { rest.push_back(r); continue; }
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; ++n; }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    cudaGetLastError();
+    h->recs.swap(rest);
+    *total_ms = ms;
+    *launches = n;
+    return 0;
+}
+
+extern "C" const char* tfrpn_kernel_name(int id) {
+    switch (id) {
+        case TFRPN_K_IOU_ARGMAX: return "rpn_iou_argmax_kernel";
+        case TFRPN_K_LABEL_ENCODE: return "rpn_label_encode_kernel";
+        case TFRPN_K_SELECT_MASK: return "select_mask_kernel";
+        case TFRPN_K_PROPOSAL: return "proposal_kernel";
+        default: return "?";
+    }
+}
 
 extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
     if (!out) return fail(TFRPN_ERR_BAD_ARG, "create: out is null");

@@ -60,22 +60,25 @@ static int base_anchors_host(const tfrpn_anchor_cfg* cfg, float* out) {
 
 // ------------------------------------------------------------------------------------------------
 // K1 generate_iou_map (utils/bbox_utils.py:126-150), materialised (B,N,G).  HBM-write bound:
-// 4*B*N*G bytes out.  One CTA owns TILE_N boxes of one image; boxes+areas and the image's GT
-// boxes+areas are staged in shared memory; threads walk the CONTIGUOUS output tile so every warp
-// store is one full 128-byte line.  (n,g) advance incrementally -- no integer division per element.
+// 4*B*N*G bytes out.  One CTA owns IOU_TILE_N boxes of one image and walks its CONTIGUOUS output
+// tile.  COLS variant (G <= 128): a thread keeps ONE GT box (column g = t % G) in registers for the
+// whole tile and steps over rows, R = 256/G rows per iteration, so consecutive threads still write
+// consecutive floats; per element that leaves one broadcast LDS.128 of the box row + ~14 ALU ops.
+// Generic variant: any G, (n,g) advanced incrementally, both operands from shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int IOU_THREADS = 256;
-constexpr int IOU_TILE_N = 128;
+constexpr int IOU_TILE_N = 256;
 
+template <bool COLS>
 __global__ void __launch_bounds__(IOU_THREADS) iou_map_kernel(const float4* __restrict__ boxes,
                                                               long long box_batch_stride,
                                                               const float4* __restrict__ gt, int N, int G,
                                                               float* __restrict__ out) {
     extern __shared__ float4 smem4[];
     float4* sbox = smem4;                      // [IOU_TILE_N]
-    float4* sgt = smem4 + IOU_TILE_N;          // [G]
-    float* sbarea = reinterpret_cast<float*>(sgt + G);  // [IOU_TILE_N]
-    float* sgarea = sbarea + IOU_TILE_N;       // [G]
+    float4* sgt = smem4 + IOU_TILE_N;          // [G]        (generic variant only)
+    float* sbarea = reinterpret_cast<float*>(sgt + (COLS ? 0 : G));  // [IOU_TILE_N]
+    float* sgarea = sbarea + IOU_TILE_N;       // [G]        (generic variant only)
 
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * IOU_TILE_N;
@@ -87,25 +90,37 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_map_kernel(const float4* __re
         sbarea[i] = box_area(v);
     }
     const float4* gb = gt + (long long)b * G;
-    for (int g = threadIdx.x; g < G; g += IOU_THREADS) {
-        float4 v = ldg_f4(gb + g);
-        sgt[g] = v;
-        sgarea[g] = box_area(v);
-    }
-    __syncthreads();
-
     float* o = out + ((long long)b * N + n0) * G;
-    const int total = tn * G;
-    const int dn = IOU_THREADS / G, dg = IOU_THREADS - dn * G;
-    int e = threadIdx.x;
-    int n = e / G, g = e - n * G;
+    if (COLS) {
+        const int R = IOU_THREADS / G;                 // rows per iteration
+        const int r = threadIdx.x / G, g = threadIdx.x - r * G;
+        const bool active = r < R;
+        const float4 gbx = ldg_f4(gb + g);
+        const float ga = box_area(gbx);
+        __syncthreads();
+        if (!active) return;
+        float* op = o + threadIdx.x;                   // == o + r*G + g
+        const int step = R * G;
 #pragma unroll 4
-    for (; e < total; e += IOU_THREADS) {
-        float v = iou_ref(sbox[n], sbarea[n], sgt[g], sgarea[g]);
-        stg_f1_stream(o + e, v);
-        n += dn;
-        g += dg;
-        if (g >= G) { g -= G; n += 1; }
+        for (int n = r; n < tn; n += R, op += step) stg_f1_stream(op, iou_ref(sbox[n], sbarea[n], gbx, ga));
+    } else {
+        for (int g = threadIdx.x; g < G; g += IOU_THREADS) {
+            float4 v = ldg_f4(gb + g);
+            sgt[g] = v;
+            sgarea[g] = box_area(v);
+        }
+        __syncthreads();
+        const int total = tn * G;
+        const int dn = IOU_THREADS / G, dg = IOU_THREADS - dn * G;
+        int e = threadIdx.x;
+        int n = e / G, g = e - n * G;
+#pragma unroll 4
+        for (; e < total; e += IOU_THREADS) {
+            stg_f1_stream(o + e, iou_ref(sbox[n], sbarea[n], sgt[g], sgarea[g]));
+            n += dn;
+            g += dg;
+            if (g >= G) { g -= G; n += 1; }
+        }
     }
 }
 
@@ -228,17 +243,20 @@ extern "C" int tfrpn_iou_map(const float* boxes, int boxes_batched, const float*
     if (B == 0 || N == 0 || G == 0) return 0;
     if (B > 65535) return fail(TFRPN_ERR_UNSUPPORTED, "iou_map: B > 65535");
     if (!aligned16(boxes) || !aligned16(gt_boxes)) return fail(TFRPN_ERR_MISALIGNED, "iou_map: boxes must be 16-byte aligned");
-    size_t smem = (size_t)(IOU_TILE_N + G) * (sizeof(float4) + sizeof(float));
+    const bool cols = G <= 128;
+    size_t smem = (size_t)(IOU_TILE_N + (cols ? 0 : G)) * (sizeof(float4) + sizeof(float));
     if (smem > 200 * 1024) return fail(TFRPN_ERR_UNSUPPORTED, "iou_map: G=%d too large for shared memory", G);
     static thread_local bool attr_set = false;
     if (smem > 48 * 1024 && !attr_set) {
-        TFRPN_CHECK_CUDA(cudaFuncSetAttribute(iou_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TFRPN_CHECK_CUDA(cudaFuncSetAttribute(iou_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
     dim3 grid((N + IOU_TILE_N - 1) / IOU_TILE_N, B);
-    iou_map_kernel<<<grid, IOU_THREADS, smem, as_stream(s)>>>(
-        reinterpret_cast<const float4*>(boxes), boxes_batched ? (long long)N : 0LL,
-        reinterpret_cast<const float4*>(gt_boxes), N, G, out);
+    const float4* b4 = reinterpret_cast<const float4*>(boxes);
+    const float4* g4 = reinterpret_cast<const float4*>(gt_boxes);
+    const long long bstride = boxes_batched ? (long long)N : 0LL;
+    if (cols) iou_map_kernel<true><<<grid, IOU_THREADS, smem, as_stream(s)>>>(b4, bstride, g4, N, G, out);
+    else iou_map_kernel<false><<<grid, IOU_THREADS, smem, as_stream(s)>>>(b4, bstride, g4, N, G, out);
     TFRPN_AFTER_LAUNCH("iou_map_kernel");
     return 0;
 }

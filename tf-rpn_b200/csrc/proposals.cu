@@ -12,6 +12,7 @@
 //     thread sweeps serially; stops at max_output_size like TF's loop does.
 //   In the fused mode boxes are decoded (+clipped) on the fly for the candidates only.
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -44,7 +45,7 @@ struct PropParams {
     float4* gathered;
     int rows, max_out;
     int mo_pad;  // max_out rounded up to a multiple of 4 (keeps the carve 16-byte aligned)
-    float iou_thr;
+    IouThreshold iou_thr;
     int clip_out;
     float4* out_boxes;
     float* out_scores;
@@ -84,18 +85,24 @@ __device__ __forceinline__ unsigned int block_excl_scan(unsigned int v, PropShar
     return r;
 }
 
-// TF CombinedNonMaxSuppression IOU on canonicalised boxes ([TF-internal]); c = (ymin,xmin,ymax,xmax)
-__device__ __forceinline__ bool nms_suppresses(float4 ci, float ai, float4 cj, float aj, float thr) {
-    float iou = 0.0f;
+// TF CombinedNonMaxSuppression IOU on canonicalised boxes ([TF-internal]); c = (ymin,xmin,ymax,xmax).
+// Returns IOU(i,j) > thr exactly as TF evaluates it: 0 if either area <= 0; otherwise
+// RN(inter / ((ai + aj) - inter)) > thr, decided without the division (common.cuh: iou_exceeds).
+__device__ __forceinline__ bool nms_suppresses(float4 ci, float ai, float4 cj, float aj, const IouThreshold& t) {
     if (ai > 0.0f && aj > 0.0f) {
         float iymin = fmaxf(ci.x, cj.x), ixmin = fmaxf(ci.y, cj.y);
         float iymax = fminf(ci.z, cj.z), ixmax = fminf(ci.w, cj.w);
         float inter = __fmul_rn(fmaxf(__fsub_rn(iymax, iymin), 0.0f), fmaxf(__fsub_rn(ixmax, ixmin), 0.0f));
-        // inter == 0  =>  0 / (ai + aj) == +0 exactly, skip the divide
-        if (inter != 0.0f) iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+        // inter == 0  =>  IOU == +0 exactly (union >= max(ai, aj) > 0)
+        if (inter != 0.0f) return iou_exceeds(inter, __fsub_rn(__fadd_rn(ai, aj), inter), t);
     }
-    return iou > thr;
+    return 0.0f > t.thr;
 }
+
+// physical index of counter (digit d, warp w): digit-major like the scan order, one pad word per
+// 32 entries so that the 32 lanes of a warp (same w, different d) hit 32 different banks
+__device__ __forceinline__ int cnt_index(uint32_t d, int w) { return (int)(d * 33u) + w; }
+constexpr int CNT_WORDS = 256 * 33;
 
 __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     extern __shared__ float4 smem4[];
@@ -108,8 +115,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     uint32_t* idxA = keyA + p.kcap;
     uint32_t* keyB = idxA + p.kcap;
     uint32_t* idxB = keyB + p.kcap;
-    unsigned int* cnt = idxB + p.kcap;                 // [256 * PR_WARPS]
-    float4* kbox = reinterpret_cast<float4*>(cnt + 256 * PR_WARPS);  // [max_out]
+    unsigned int* cnt = idxB + p.kcap;                 // [CNT_WORDS]
+    float4* kbox = reinterpret_cast<float4*>(cnt + CNT_WORDS);  // [max_out]
     float4* cbox = kbox + p.mo_pad;                   // [NMS_CHUNK]
     float* karea = reinterpret_cast<float*>(cbox + NMS_CHUNK);  // [max_out]
     float* carea = karea + p.mo_pad;                  // [NMS_CHUNK]
@@ -216,46 +223,43 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
         __syncthreads();
 
         // ---- phase 3: stable LSD radix sort, 4 x 8 bits, (keyA,idxA) <-> (keyB,idxB) -------------
+        // Each warp owns a contiguous segment; counters are per (digit, warp); an exclusive scan in
+        // (digit, warp) order turns them into scatter bases; match.any ranks equal digits in a chunk.
         {
             const int seg = (((K + PR_WARPS - 1) / PR_WARPS) + 31) & ~31;
             const int start = min(warp * seg, K), end = min(start + seg, K);
             uint32_t *kin = keyA, *vin = idxA, *kout = keyB, *vout = idxB;
             for (int sft = 0; sft < 32; sft += 8) {
-                for (int i = tid; i < 256 * PR_WARPS; i += PR_THREADS) cnt[i] = 0u;
+                for (int i = tid; i < CNT_WORDS; i += PR_THREADS) cnt[i] = 0u;
                 __syncthreads();
-                for (int e0 = start; e0 < end; e0 += 32) {
-                    const int e = e0 + lane;
-                    const bool v = e < end;
-                    const uint32_t d = v ? ((kin[e] >> sft) & 255u) : (256u + lane);
-                    const unsigned peers = __match_any_sync(0xffffffffu, d);
-                    if (v && lane == __ffs(peers) - 1) cnt[d * PR_WARPS + warp] += __popc(peers);
-                    __syncwarp();
-                }
+                for (int e = start + lane; e < end; e += 32) atomicAdd(&cnt[cnt_index((kin[e] >> sft) & 255u, warp)], 1u);
                 __syncthreads();
-                {   // exclusive scan of cnt in (digit, warp) order: 8 entries per thread
-                    unsigned int loc[8], s = 0;
+                {   // exclusive scan over the 8192 logical counters, 8 consecutive ones per thread
+                    unsigned int loc[8], sum = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { loc[q] = cnt[tid * 8 + q]; s += loc[q]; }
+                    for (int q = 0; q < 8; ++q) { const int L = tid * 8 + q; loc[q] = cnt[L + (L >> 5)]; sum += loc[q]; }
                     unsigned int tot;
-                    unsigned int ex = block_excl_scan(s, &sh, &tot);
+                    unsigned int ex = block_excl_scan(sum, &sh, &tot);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { cnt[tid * 8 + q] = ex; ex += loc[q]; }
+                    for (int q = 0; q < 8; ++q) { const int L = tid * 8 + q; cnt[L + (L >> 5)] = ex; ex += loc[q]; }
                 }
                 __syncthreads();
                 for (int e0 = start; e0 < end; e0 += 32) {
                     const int e = e0 + lane;
                     const bool v = e < end;
                     const uint32_t key = v ? kin[e] : 0u;
+                    const uint32_t val = v ? vin[e] : 0u;
                     const uint32_t d = v ? ((key >> sft) & 255u) : (256u + lane);
                     const unsigned peers = __match_any_sync(0xffffffffu, d);
+                    const int ci = cnt_index(d & 255u, warp);
                     unsigned int basepos = 0;
-                    if (v) basepos = cnt[d * PR_WARPS + warp];
+                    if (v) basepos = cnt[ci];
                     __syncwarp();
                     if (v) {
                         const unsigned int rank = __popc(peers & ((1u << lane) - 1u));
-                        if (lane == __ffs(peers) - 1) cnt[d * PR_WARPS + warp] = basepos + __popc(peers);
+                        if (rank == 0) cnt[ci] = basepos + __popc(peers);
                         kout[basepos + rank] = key;
-                        vout[basepos + rank] = vin[e];
+                        vout[basepos + rank] = val;
                     }
                     __syncwarp();
                 }
@@ -278,19 +282,31 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
         }
 
         // ---- phase 4b: greedy NMS over the sorted candidates ------------------------------------
-        const float thr = p.iou_thr;
+        // Rounds of NMS_CHUNK candidates in score order.  The next round's boxes are fetched (and, in
+        // the fused mode, their deltas gathered) while the current round is being resolved.
+        const IouThreshold thr = p.iou_thr;
+        auto fetch = [&](int pos, float4& a, float4& d, uint32_t& idx) {
+            if (pos + tid < K && tid < NMS_CHUNK) {
+                idx = idxA[pos + tid];
+                if (p.mode == MODE_PROPOSALS) {
+                    d = ldg_f4(p.reg + (long long)b * N + idx);
+                    a = ldg_f4(p.anchors + idx);
+                } else {
+                    a = ldg_f4(p.boxes + (long long)b * p.box_stride + idx);
+                }
+            }
+        };
+        float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nd = na;
+        uint32_t nidx = 0u;
+        fetch(0, na, nd, nidx);
         for (int pos = 0; pos < K && nkept < p.max_out; pos += NMS_CHUNK) {
             const int C = min(NMS_CHUNK, K - pos);
-            float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint32_t my_idx = 0u;
+            float4 raw = na;
+            const uint32_t my_idx = nidx;
             if (tid < C) {
-                my_idx = idxA[pos + tid];
                 if (p.mode == MODE_PROPOSALS) {
-                    float4 d = mul4(ldg_f4(p.reg + (long long)b * N + my_idx), p.var);   // predictor.py:55
-                    raw = decode_ref(ldg_f4(p.anchors + my_idx), d);                     // predictor.py:56
+                    raw = decode_ref(na, mul4(nd, p.var));                               // predictor.py:55-56
                     if (p.clip_decoded) raw = clip01(raw);
-                } else {
-                    raw = ldg_f4(p.boxes + (long long)b * p.box_stride + my_idx);
                 }
                 float4 c = make_float4(fminf(raw.x, raw.z), fminf(raw.y, raw.w), fmaxf(raw.x, raw.z), fmaxf(raw.y, raw.w));
                 cbox[tid] = c;
@@ -298,6 +314,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 alive[tid] = 1u;
             }
             __syncthreads();
+            fetch(pos + NMS_CHUNK, na, nd, nidx);   // in flight during the tests below
             {   // candidates vs kept list: thread = (candidate c, part), kept j strided by NMS_PARTS
                 const int c = tid & (NMS_CHUNK - 1), part = tid >> 7;
                 if (c < C) {
@@ -309,41 +326,64 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 }
             }
             __syncthreads();
-            {   // intra-chunk masks: thread = (row i, 16-column group w); bit set iff i suppresses j > i
+            {   // intra-chunk predecessor masks: thread = (row i, 16-column group w);
+                // bit j set iff j < i, both alive, and j suppresses i
                 const int i = tid >> 3, w = tid & 7;
                 unsigned int bits = 0u;
-                if (i < C && alive[i]) {
+                if (i < C && alive[i] && w * 16 < i) {
                     const float4 bi = cbox[i];
                     const float ai = carea[i];
+                    const int jend = min(16, i - w * 16);
 #pragma unroll 4
-                    for (int jj = 0; jj < 16; ++jj) {
+                    for (int jj = 0; jj < jend; ++jj) {
                         const int j = w * 16 + jj;
-                        if (j > i && j < C && alive[j] && nms_suppresses(cbox[j], carea[j], bi, ai, thr)) bits |= 1u << jj;
+                        if (alive[j] && nms_suppresses(cbox[j], carea[j], bi, ai, thr)) bits |= 1u << jj;
                     }
                 }
                 mask16[i * 8 + w] = (unsigned short)bits;
             }
             __syncthreads();
-            if (tid == 0) {  // serial sweep in score order
-                unsigned int rem[4] = {0u, 0u, 0u, 0u};
-                int nk = 0;
+            if (warp == 0) {
+                // Resolve the chunk in parallel rounds (same result as the sequential greedy sweep):
+                // an undecided candidate is REMOVED if a kept predecessor suppresses it, KEPT if no
+                // undecided predecessor suppresses it, else stays undecided.  Lane l owns candidates
+                // l, 32+l, 64+l, 96+l, so ballot word q is exactly bits [32q, 32q+32).
                 const uint4* m4 = reinterpret_cast<const uint4*>(mask16);
+                uint4 pr[4];
+                unsigned U[4], Kp[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-#pragma unroll 8
-                    for (int ii = 0; ii < 32; ++ii) {
-                        const int i = w * 32 + ii;
-                        int s = -1;
-                        if (i < C && alive[i] && !((rem[w] >> ii) & 1u) && nkept + nk < p.max_out) {
-                            s = nkept + nk;
-                            ++nk;
-                            const uint4 m = m4[i];
-                            rem[0] |= m.x; rem[1] |= m.y; rem[2] |= m.z; rem[3] |= m.w;
-                        }
-                        slot[i] = s;
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    const int c = q * 32 + lane;
+                    pr[q] = m4[c];
+                    U[q] = __ballot_sync(0xffffffffu, c < C && alive[c] != 0u);
                 }
-                sh.nk = nk;
+                while ((U[0] | U[1] | U[2] | U[3]) != 0u) {
+                    unsigned nU[4], nK[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool und = (U[q] >> lane) & 1u;
+                        const unsigned hitK = (pr[q].x & Kp[0]) | (pr[q].y & Kp[1]) | (pr[q].z & Kp[2]) | (pr[q].w & Kp[3]);
+                        const unsigned hitU = (pr[q].x & U[0]) | (pr[q].y & U[1]) | (pr[q].z & U[2]) | (pr[q].w & U[3]);
+                        const bool keep = und && hitK == 0u && hitU == 0u;
+                        const bool stay = und && hitK == 0u && hitU != 0u;
+                        nK[q] = __ballot_sync(0xffffffffu, keep);
+                        nU[q] = __ballot_sync(0xffffffffu, stay);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { Kp[q] |= nK[q]; U[q] = nU[q]; }
+                }
+                // kept candidates take consecutive output slots in score order, capped at max_out
+                const int allowed = p.max_out - nkept;
+                int before = 0, total = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rank = before + __popc(Kp[q] & ((1u << lane) - 1u));
+                    const bool kept = ((Kp[q] >> lane) & 1u) && rank < allowed;
+                    slot[q * 32 + lane] = kept ? nkept + rank : -1;
+                    before += __popc(Kp[q]);
+                }
+                total = before;
+                if (lane == 0) sh.nk = min(total, allowed);
             }
             __syncthreads();
             if (tid < C && slot[tid] >= 0) {
@@ -373,10 +413,22 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     if (tid == 0) p.valid[b] = nkept;
 }
 
+static IouThreshold make_threshold(float thr) {
+    IouThreshold t;
+    t.thr = thr;
+    t.fast = (thr >= 1e-30f && thr <= 1e30f) ? 1 : 0;
+    const float nxt = nextafterf(thr, INFINITY);
+    t.mid = ((double)thr + (double)nxt) * 0.5;   // exact: 25 significant bits
+    uint32_t nb;
+    memcpy(&nb, &nxt, 4);
+    t.tie_up = ((nb & 1u) == 0u) ? 1 : 0;        // a tie rounds to the even mantissa
+    return t;
+}
+
 static size_t prop_smem_bytes(int kcap, int max_out) {
     max_out = (max_out + 3) & ~3;
     size_t s = (size_t)kcap * 16;                 // keyA, idxA, keyB, idxB
-    s += (size_t)256 * PR_WARPS * 4;              // cnt
+    s += (size_t)CNT_WORDS * 4;                   // cnt
     s += (size_t)(max_out + NMS_CHUNK) * (16 + 4);  // kbox+cbox, karea+carea
     s += (size_t)NMS_CHUNK * (4 + 4 + 16);        // alive, slot, mask16
     return s + 16;
@@ -403,7 +455,7 @@ static int plan(PropParams& p, size_t* smem) {
     return 0;
 }
 
-static int launch(PropParams& p, int B, cudaStream_t st) {
+static int launch(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
     size_t smem = 0;
     p.mo_pad = (p.max_out + 3) & ~3;
     if (int rc = plan(p, &smem)) return rc;
@@ -412,7 +464,9 @@ static int launch(PropParams& p, int B, cudaStream_t st) {
         TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROP_SMEM_LIMIT));
         attr_set = true;
     }
+    prof_begin(h, TFRPN_K_PROPOSAL, st);
     proposal_kernel<<<B, PR_THREADS, smem, st>>>(p);
+    prof_end(h, st);
     TFRPN_AFTER_LAUNCH("proposal_kernel");
     return 0;
 }
@@ -423,7 +477,6 @@ using namespace tfrpn;
 
 extern "C" int tfrpn_topk(tfrpn_handle h, const float* scores, int B, int N, int k, float* values, int32_t* indices,
                           const float* boxes_or_null, int boxes_batched, float* gathered_or_null, tfrpn_stream s) {
-    (void)h;
     if (!scores || !values || !indices) return fail(TFRPN_ERR_BAD_ARG, "topk: null pointer");
     if (B < 0 || N < 0 || k < 0) return fail(TFRPN_ERR_BAD_ARG, "topk: negative shape");
     if (k > N) return fail(TFRPN_ERR_BAD_ARG, "topk: k=%d > N=%d (tf.nn.top_k raises InvalidArgumentError too)", k, N);
@@ -437,13 +490,12 @@ extern "C" int tfrpn_topk(tfrpn_handle h, const float* scores, int B, int N, int
     p.boxes = reinterpret_cast<const float4*>(boxes_or_null); p.box_stride = boxes_batched ? N : 0;
     p.values = values; p.indices = indices; p.gathered = reinterpret_cast<float4*>(gathered_or_null);
     p.max_out = 0; p.rows = 0;
-    return launch(p, B, as_stream(s));
+    return launch(h, p, B, as_stream(s));
 }
 
 extern "C" int tfrpn_nms(tfrpn_handle h, const float* boxes, const float* scores, int B, int K, const tfrpn_nms_cfg* cfg,
                          float* out_boxes, float* out_scores, float* out_classes, int32_t* valid,
                          int32_t* keep_idx_or_null, tfrpn_stream s) {
-    (void)h;
     if (!boxes || !scores || !cfg || !out_boxes || !out_scores || !valid) return fail(TFRPN_ERR_BAD_ARG, "nms: null pointer");
     if (B < 0 || K < 0) return fail(TFRPN_ERR_BAD_ARG, "nms: negative shape");
     if (cfg->max_output_size_per_class <= 0 || cfg->max_total_size <= 0)
@@ -457,16 +509,15 @@ extern "C" int tfrpn_nms(tfrpn_handle h, const float* boxes, const float* scores
     p.boxes = reinterpret_cast<const float4*>(boxes); p.box_stride = K;
     p.rows = cfg->pad_per_class ? min(cfg->max_total_size, cfg->max_output_size_per_class) : cfg->max_total_size;
     p.max_out = min(cfg->max_output_size_per_class, p.rows);
-    p.iou_thr = cfg->iou_threshold; p.clip_out = cfg->clip_boxes;
+    p.iou_thr = make_threshold(cfg->iou_threshold); p.clip_out = cfg->clip_boxes;
     p.out_boxes = reinterpret_cast<float4*>(out_boxes); p.out_scores = out_scores; p.out_classes = out_classes;
     p.valid = valid; p.keep_idx = keep_idx_or_null;
-    return launch(p, B, as_stream(s));
+    return launch(h, p, B, as_stream(s));
 }
 
 extern "C" int tfrpn_proposals(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B,
                                int N, const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores,
                                int32_t* valid, int32_t* keep_idx_or_null, tfrpn_stream s) {
-    (void)h;
     if (!rpn_reg || !rpn_cls || !anchors || !cfg || !out_boxes || !out_scores || !valid)
         return fail(TFRPN_ERR_BAD_ARG, "proposals: null pointer");
     if (B < 0 || N < 0) return fail(TFRPN_ERR_BAD_ARG, "proposals: negative shape");
@@ -480,8 +531,8 @@ extern "C" int tfrpn_proposals(tfrpn_handle h, const float* rpn_reg, const float
     p.var = make_float4(cfg->variances[0], cfg->variances[1], cfg->variances[2], cfg->variances[3]);
     p.clip_decoded = cfg->clip;
     p.rows = cfg->post_nms_topn; p.max_out = cfg->post_nms_topn;
-    p.iou_thr = cfg->nms_iou_threshold; p.clip_out = 1;  // combined NMS default clip_boxes=True
+    p.iou_thr = make_threshold(cfg->nms_iou_threshold); p.clip_out = 1;  // combined NMS default clip_boxes=True
     p.out_boxes = reinterpret_cast<float4*>(out_boxes); p.out_scores = out_scores; p.out_classes = nullptr;
     p.valid = valid; p.keep_idx = keep_idx_or_null;
-    return launch(p, B, as_stream(s));
+    return launch(h, p, B, as_stream(s));
 }

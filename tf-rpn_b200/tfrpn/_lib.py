@@ -49,6 +49,9 @@ PROTOTYPES = {
     "tfrpn_reserve": (I, [P, I, I, I, I]),
     "tfrpn_workspace_bytes": (C.c_size_t, [I, I, I, I]),
     "tfrpn_launch_count": (C.c_uint64, []),
+    "tfrpn_profile_enable": (I, [P, I]),
+    "tfrpn_profile_read": (I, [P, I, C.POINTER(C.c_double), C.POINTER(I)]),
+    "tfrpn_kernel_name": (C.c_char_p, [I]),
     "tfrpn_base_anchors_host": (I, [C.POINTER(AnchorCfg), P]),
     "tfrpn_anchors": (I, [C.POINTER(AnchorCfg), P, P]),
     "tfrpn_iou_map": (I, [P, I, P, I, I, I, P, P]),
