@@ -2,15 +2,20 @@
 //
 // Replaces tf.nn.top_k + tf.gather (predictor.py:58-60), non_max_suppression ->
 // tf.image.combined_non_max_suppression (utils/bbox_utils.py:48-70) and their composition
-// (SURVEY.md 8a row P).  Phases inside the CTA (all in shared memory):
-//   1 radix SELECT of the k-th largest score key (MSB-first, 8 bits/pass, early exit)
-//   2 ORDERED compaction of the selected entries (ascending index, so equal scores stay in
-//     index order: [TF-internal] top_k returns the lower index first)
-//   3 stable LSD radix SORT by score descending (4 x 8-bit passes, match.any ranking)
-//   4 top-k outputs, or chunked greedy NMS in score order: 128 candidates per round are tested
-//     against the kept list, then against each other through 128-bit suppression masks that one
-//     thread sweeps serially; stops at max_output_size like TF's loop does.
-//   In the fused mode boxes are decoded (+clipped) on the fly for the candidates only.
+// (SURVEY.md 8a row P).
+//
+// Order: every entry gets the unique 64-bit composite  (orderable(score) << 32) | ~index , so
+// "larger composite" == "higher score, and among equal scores the LOWER index" -- the order of
+// tf.nn.top_k and the order in which TF's NMS pops candidates ([TF-internal]; ties documented in
+// the oracle).  NMS is lazy: it consumes candidates in BATCHES of 1024 ranks and usually stops
+// (max_output_size kept) inside the first batch, so the other ~5000 of the pre-NMS top-6000 are
+// never sorted, gathered or decoded.  Per batch, inside the CTA:
+//   1 radix SELECT (MSB first, 8 bits/pass, early exit) of the composite at rank `hi`
+//   2 unordered COMPACTION of the entries with rank in [lo, hi) into shared memory
+//   3 BITONIC SORT of those <= 1024 composites, one per thread (shuffles below stride 32)
+//   4 top-k outputs, or greedy NMS rounds of 128 candidates: test against the kept list, build
+//     predecessor masks inside the round, resolve them in one warp with ballots.
+//   In the fused mode boxes are decoded (+clipped) on the fly, for the examined candidates only.
 #include <math.h>
 #include <string.h>
 
@@ -20,6 +25,7 @@ namespace tfrpn {
 
 constexpr int PR_THREADS = 1024;
 constexpr int PR_WARPS = PR_THREADS / 32;
+constexpr int BATCH = PR_THREADS;   // ranks sorted per batch: one composite per thread
 constexpr int NMS_CHUNK = 128;
 constexpr int NMS_PARTS = PR_THREADS / NMS_CHUNK;  // 8
 
@@ -27,10 +33,9 @@ enum { MODE_TOPK = 0, MODE_NMS = 1, MODE_PROPOSALS = 2 };
 
 struct PropParams {
     int mode;
-    int N;     // entries per image
-    int k;     // requested top-k (<= N)
-    int kcap;  // shared-memory sort capacity (entries)
-    int staged;
+    int N;       // entries per image
+    int k;       // requested top-k (<= N)
+    int staged;  // score keys staged in shared memory (N * 4 bytes)
     const float* scores;  // (B,N)
     int use_sthr;
     float score_threshold;
@@ -55,32 +60,34 @@ struct PropParams {
 };
 
 struct PropShared {
+    unsigned int hist[256];
     unsigned int wtot[PR_WARPS];
     unsigned int digit, remaining, bin_count;
     unsigned int count;
     int nk;
 };
 
-// sort key: descending score == ascending ~orderable(score)
+// score -> sortable key; entries at or below the score threshold get key 0 (below every real key)
 __device__ __forceinline__ uint32_t score_key(float s, int use_sthr, float sthr) {
     if (use_sthr && !(s > sthr)) return 0u;
     return orderable(s);
 }
+__device__ __forceinline__ unsigned long long make_comp(uint32_t key, int i) {
+    return ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+}
 
-// exclusive block scan of one unsigned per thread (1024 threads); returns exclusive prefix, total in *total
-__device__ __forceinline__ unsigned int block_excl_scan(unsigned int v, PropShared* sh, unsigned int* total) {
+// block-wide sum of one unsigned per thread
+__device__ __forceinline__ unsigned int block_sum(unsigned int v, PropShared* sh) {
     unsigned int incl = (unsigned int)warp_incl_scan((int)v);
     if (lane_id() == 31) sh->wtot[warp_id()] = incl;
     __syncthreads();
     if (warp_id() == 0) {
         unsigned int w = sh->wtot[lane_id()];
         unsigned int wi = (unsigned int)warp_incl_scan((int)w);
-        sh->wtot[lane_id()] = wi - w;
         if (lane_id() == 31) sh->count = wi;
     }
     __syncthreads();
-    unsigned int r = sh->wtot[warp_id()] + incl - v;
-    *total = sh->count;
+    unsigned int r = sh->count;
     __syncthreads();
     return r;
 }
@@ -99,10 +106,31 @@ __device__ __forceinline__ bool nms_suppresses(float4 ci, float ai, float4 cj, f
     return 0.0f > t.thr;
 }
 
-// physical index of counter (digit d, warp w): digit-major like the scan order, one pad word per
-// 32 entries so that the 32 lanes of a warp (same w, different d) hit 32 different banks
-__device__ __forceinline__ int cnt_index(uint32_t d, int w) { return (int)(d * 33u) + w; }
-constexpr int CNT_WORDS = 256 * 33;
+// descending bitonic sort of PR_THREADS composites, one per thread; thread t ends with rank t.
+// Strides < 32 use shuffles; strides >= 32 go through a double-buffered shared array (1 barrier each).
+__device__ __forceinline__ unsigned long long bitonic_sort_desc(unsigned long long v, unsigned long long* buf) {
+    const int t = threadIdx.x;
+    int flip = 0;
+    for (int k = 2; k <= PR_THREADS; k <<= 1) {
+        const bool desc = (t & k) == 0;
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long pv;
+            if (j >= 32) {
+                unsigned long long* bb = buf + flip * PR_THREADS;
+                bb[t] = v;
+                __syncthreads();
+                pv = bb[t ^ j];
+                flip ^= 1;
+            } else {
+                pv = __shfl_xor_sync(0xffffffffu, v, j);
+            }
+            const bool lower = (t & j) == 0;
+            const bool keep_max = (lower == desc);
+            v = keep_max ? max(v, pv) : min(v, pv);
+        }
+    }
+    return v;
+}
 
 __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     extern __shared__ float4 smem4[];
@@ -111,19 +139,16 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     const int b = blockIdx.x, N = p.N;
     const float* scores = p.scores + (long long)b * N;
 
-    uint32_t* keyA = reinterpret_cast<uint32_t*>(smem4);
-    uint32_t* idxA = keyA + p.kcap;
-    uint32_t* keyB = idxA + p.kcap;
-    uint32_t* idxB = keyB + p.kcap;
-    unsigned int* cnt = idxB + p.kcap;                 // [CNT_WORDS]
-    float4* kbox = reinterpret_cast<float4*>(cnt + CNT_WORDS);  // [max_out]
-    float4* cbox = kbox + p.mo_pad;                   // [NMS_CHUNK]
-    float* karea = reinterpret_cast<float*>(cbox + NMS_CHUNK);  // [max_out]
-    float* carea = karea + p.mo_pad;                  // [NMS_CHUNK]
-    unsigned int* alive = reinterpret_cast<unsigned int*>(carea + NMS_CHUNK);  // [NMS_CHUNK]
-    int* slot = reinterpret_cast<int*>(alive + NMS_CHUNK);                     // [NMS_CHUNK]
-    unsigned short* mask16 = reinterpret_cast<unsigned short*>(slot + NMS_CHUNK);  // [NMS_CHUNK][8]
-    uint32_t* skeys = keyB;  // staged keys alias sort buffer B (free until the first sort pass)
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(smem4);   // [2 * BATCH]
+    uint32_t* sidx = reinterpret_cast<uint32_t*>(sortbuf + 2 * BATCH);            // [BATCH] sorted indices
+    float4* kbox = reinterpret_cast<float4*>(sidx + BATCH);                       // [mo_pad]
+    float4* cbox = kbox + p.mo_pad;                                               // [NMS_CHUNK]
+    float* karea = reinterpret_cast<float*>(cbox + NMS_CHUNK);                    // [mo_pad]
+    float* carea = karea + p.mo_pad;                                              // [NMS_CHUNK]
+    unsigned int* alive = reinterpret_cast<unsigned int*>(carea + NMS_CHUNK);     // [NMS_CHUNK]
+    int* slot = reinterpret_cast<int*>(alive + NMS_CHUNK);                        // [NMS_CHUNK]
+    unsigned short* mask16 = reinterpret_cast<unsigned short*>(slot + NMS_CHUNK); // [NMS_CHUNK][8]
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(mask16 + NMS_CHUNK * 8);        // [N] when staged
 
     // ---- phase 0: stage keys, count entries above the score threshold ---------------------------
     unsigned int my_valid = 0;
@@ -133,43 +158,50 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
         my_valid += (key != 0u) ? 1u : 0u;
     }
     int M = N;
-    if (p.use_sthr) {
-        unsigned int total;
-        block_excl_scan(my_valid, &sh, &total);
-        M = (int)total;
-    } else {
-        __syncthreads();
-    }
-    const int K = min(p.k, M);  // entries that get sorted
+    if (p.use_sthr) M = (int)block_sum(my_valid, &sh);
+    else __syncthreads();
+    const int K = min(p.k, M);  // ranks that may be consumed
     int nkept = 0;
+    const IouThreshold thr = p.iou_thr;
 
-    if (K > 0) {
-        // ---- phase 1: radix select -- find (shift, P, need_eq): entry selected iff
-        //      (key>>shift) > P, or == P and it is among the first need_eq such entries by index
-        uint32_t prefix = 0u;
-        unsigned int r = (unsigned int)K;
-        int shift = 24;
-        bool take_all = (K == N);
-        if (!take_all) {
-            for (int pass = 0; pass < 4; ++pass) {
-                for (int i = tid; i < 256; i += PR_THREADS) cnt[i] = 0u;
+    auto key_at = [&](int i) -> uint32_t {
+        return p.staged ? skeys[i] : score_key(scores[i], p.use_sthr, p.score_threshold);
+    };
+
+    // rule "rank < r":  (comp >> shift) >= P   (the lo rule of the first batch selects nothing)
+    int lo_shift = 0;
+    unsigned long long lo_P = ~0ull;
+    bool have_lo = false;
+
+    for (int lo = 0; lo < K; lo += BATCH) {
+        const int hi = min(lo + BATCH, K);
+        // ---- 1. radix select of the composite at rank hi --------------------------------------
+        int shift = 0;
+        unsigned long long P = 0ull;          // hi == N: everything is selected
+        if (hi < N) {
+            unsigned long long prefix = 0ull;
+            unsigned int r = (unsigned int)hi;
+            shift = 56;
+            for (int pass = 0; pass < 8; ++pass) {
+                if (tid < 256) sh.hist[tid] = 0u;
                 __syncthreads();
+                const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
                 for (int i = tid; i < N; i += PR_THREADS) {
-                    uint32_t key = p.staged ? skeys[i] : score_key(scores[i], p.use_sthr, p.score_threshold);
-                    if (pass == 0 || ((key ^ prefix) >> (shift + 8)) == 0u) atomicAdd(&cnt[(key >> shift) & 255u], 1u);
+                    const unsigned long long c = make_comp(key_at(i), i);
+                    if (((c ^ prefix) & himask) == 0ull) atomicAdd(&sh.hist[(unsigned)(c >> shift) & 255u], 1u);
                 }
                 __syncthreads();
-                if (tid < 32) {
+                if (tid < 32) {   // lane l owns digits [248-8l, 255-8l], scanned from the top
                     const int top = 255 - 8 * lane;
                     unsigned int s = 0;
 #pragma unroll
-                    for (int d = 0; d < 8; ++d) s += cnt[top - d];
-                    unsigned int incl = (unsigned int)warp_incl_scan((int)s);
-                    unsigned int excl = incl - s;
+                    for (int d = 0; d < 8; ++d) s += sh.hist[top - d];
+                    const unsigned int incl = (unsigned int)warp_incl_scan((int)s);
+                    const unsigned int excl = incl - s;
                     if (excl < r && r <= incl) {
                         unsigned int acc = excl;
                         for (int d = 0; d < 8; ++d) {
-                            unsigned int c = cnt[top - d];
+                            const unsigned int c = sh.hist[top - d];
                             if (acc + c >= r) {
                                 sh.digit = (unsigned)(top - d);
                                 sh.remaining = r - acc;
@@ -181,113 +213,62 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                     }
                 }
                 __syncthreads();
-                prefix |= sh.digit << shift;
+                prefix |= (unsigned long long)sh.digit << shift;
                 r = sh.remaining;
-                const bool done = (sh.bin_count == r);
+                const bool done = (sh.bin_count == r);   // the whole bin is taken: stop refining
                 __syncthreads();
-                if (done || pass == 3) break;
+                if (done || pass == 7) break;
                 shift -= 8;
             }
+            P = prefix >> shift;
         }
-        const uint32_t P = take_all ? 0u : (prefix >> shift);
-        const unsigned int need_eq = take_all ? 0u : r;
-
-        // ---- phase 2: ordered compaction into (keyA, idxA), ascending index ---------------------
-        unsigned int run_gt = 0, run_eq = 0;
+        // ---- 2. compaction of ranks [lo, hi) (any order: composites are unique) -----------------
+        if (tid == 0) sh.count = 0u;
+        sortbuf[tid] = 0ull;                    // padding sorts last
+        __syncthreads();
         for (int base = 0; base < N; base += PR_THREADS) {
             const int i = base + tid;
-            uint32_t key = 0u;
-            bool gt = false, eq = false;
+            bool take = false;
+            unsigned long long c = 0ull;
             if (i < N) {
-                key = p.staged ? skeys[i] : score_key(scores[i], p.use_sthr, p.score_threshold);
-                if (take_all) gt = true;
-                else {
-                    uint32_t hs = key >> shift;
-                    gt = hs > P;
-                    eq = hs == P;
-                }
+                c = make_comp(key_at(i), i);
+                take = ((c >> shift) >= P) && !(have_lo && ((c >> lo_shift) >= lo_P));
             }
-            unsigned int tot;
-            unsigned int ex = block_excl_scan((gt ? 1u : 0u) | (eq ? 0x10000u : 0u), &sh, &tot);
-            const unsigned int gt_before = run_gt + (ex & 0xFFFFu);
-            const unsigned int eq_before = run_eq + (ex >> 16);
-            if (gt || (eq && eq_before < need_eq)) {
-                unsigned int pos = gt_before + min(eq_before, need_eq);
-                keyA[pos] = ~key;
-                idxA[pos] = (uint32_t)i;
+            const unsigned bal = __ballot_sync(0xffffffffu, take);
+            if (bal != 0u) {
+                unsigned int basepos = 0;
+                if (lane == __ffs(bal) - 1) basepos = atomicAdd(&sh.count, (unsigned)__popc(bal));
+                basepos = __shfl_sync(0xffffffffu, basepos, __ffs(bal) - 1);
+                if (take) sortbuf[basepos + __popc(bal & ((1u << lane) - 1u))] = c;
             }
-            run_gt += tot & 0xFFFFu;
-            run_eq += tot >> 16;
-            if (run_gt + min(run_eq, need_eq) >= (unsigned int)K) break;
         }
         __syncthreads();
+        // ---- 3. sort: thread t gets the composite of rank lo + t ---------------------------------
+        unsigned long long mine = sortbuf[tid];
+        __syncthreads();
+        mine = bitonic_sort_desc(mine, sortbuf);
+        const int nb = hi - lo;                 // entries in this batch
+        const uint32_t my_i = 0xFFFFFFFFu - (uint32_t)(mine & 0xFFFFFFFFull);
+        lo_shift = shift; lo_P = P; have_lo = true;
 
-        // ---- phase 3: stable LSD radix sort, 4 x 8 bits, (keyA,idxA) <-> (keyB,idxB) -------------
-        // Each warp owns a contiguous segment; counters are per (digit, warp); an exclusive scan in
-        // (digit, warp) order turns them into scatter bases; match.any ranks equal digits in a chunk.
-        {
-            const int seg = (((K + PR_WARPS - 1) / PR_WARPS) + 31) & ~31;
-            const int start = min(warp * seg, K), end = min(start + seg, K);
-            uint32_t *kin = keyA, *vin = idxA, *kout = keyB, *vout = idxB;
-            for (int sft = 0; sft < 32; sft += 8) {
-                for (int i = tid; i < CNT_WORDS; i += PR_THREADS) cnt[i] = 0u;
-                __syncthreads();
-                for (int e = start + lane; e < end; e += 32) atomicAdd(&cnt[cnt_index((kin[e] >> sft) & 255u, warp)], 1u);
-                __syncthreads();
-                {   // exclusive scan over the 8192 logical counters, 8 consecutive ones per thread
-                    unsigned int loc[8], sum = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) { const int L = tid * 8 + q; loc[q] = cnt[L + (L >> 5)]; sum += loc[q]; }
-                    unsigned int tot;
-                    unsigned int ex = block_excl_scan(sum, &sh, &tot);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) { const int L = tid * 8 + q; cnt[L + (L >> 5)] = ex; ex += loc[q]; }
-                }
-                __syncthreads();
-                for (int e0 = start; e0 < end; e0 += 32) {
-                    const int e = e0 + lane;
-                    const bool v = e < end;
-                    const uint32_t key = v ? kin[e] : 0u;
-                    const uint32_t val = v ? vin[e] : 0u;
-                    const uint32_t d = v ? ((key >> sft) & 255u) : (256u + lane);
-                    const unsigned peers = __match_any_sync(0xffffffffu, d);
-                    const int ci = cnt_index(d & 255u, warp);
-                    unsigned int basepos = 0;
-                    if (v) basepos = cnt[ci];
-                    __syncwarp();
-                    if (v) {
-                        const unsigned int rank = __popc(peers & ((1u << lane) - 1u));
-                        if (rank == 0) cnt[ci] = basepos + __popc(peers);
-                        kout[basepos + rank] = key;
-                        vout[basepos + rank] = val;
-                    }
-                    __syncwarp();
-                }
-                __syncthreads();
-                uint32_t* t = kin; kin = kout; kout = t;
-                t = vin; vin = vout; vout = t;
-            }
-            // 4 passes: result is back in (keyA, idxA)
-        }
-
-        // ---- phase 4a: top-k outputs (predictor.py:58-60) ------------------------------------------
+        // ---- 4a. top-k outputs (predictor.py:58-60) -------------------------------------------
         if (p.mode == MODE_TOPK) {
-            for (int rnk = tid; rnk < K; rnk += PR_THREADS) {
-                const uint32_t idx = idxA[rnk];
-                p.values[(long long)b * p.k + rnk] = scores[idx];
-                p.indices[(long long)b * p.k + rnk] = (int)idx;
-                if (p.gathered) p.gathered[(long long)b * p.k + rnk] = ldg_f4(p.boxes + (long long)b * p.box_stride + idx);
+            if (tid < nb) {
+                const long long o = (long long)b * p.k + lo + tid;
+                p.values[o] = scores[my_i];
+                p.indices[o] = (int)my_i;
+                if (p.gathered) p.gathered[o] = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
             }
-            return;
+            __syncthreads();   // sortbuf is rewritten by the next batch
+            continue;
         }
 
-        // ---- phase 4b: greedy NMS over the sorted candidates ------------------------------------
-        // Rounds of NMS_CHUNK candidates in score order.  The next round's boxes are fetched (and, in
-        // the fused mode, their deltas gathered) while the current round is being resolved.
-        const IouThreshold thr = p.iou_thr;
+        // ---- 4b. greedy NMS rounds over this batch ---------------------------------------------
+        sidx[tid] = my_i;
+        __syncthreads();
         auto fetch = [&](int pos, float4& a, float4& d, uint32_t& idx) {
-            if (pos + tid < K && tid < NMS_CHUNK) {
-                idx = idxA[pos + tid];
+            if (tid < NMS_CHUNK && pos + tid < nb) {
+                idx = sidx[pos + tid];
                 if (p.mode == MODE_PROPOSALS) {
                     d = ldg_f4(p.reg + (long long)b * N + idx);
                     a = ldg_f4(p.anchors + idx);
@@ -299,8 +280,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
         float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nd = na;
         uint32_t nidx = 0u;
         fetch(0, na, nd, nidx);
-        for (int pos = 0; pos < K && nkept < p.max_out; pos += NMS_CHUNK) {
-            const int C = min(NMS_CHUNK, K - pos);
+        for (int pos = 0; pos < nb && nkept < p.max_out; pos += NMS_CHUNK) {
+            const int C = min(NMS_CHUNK, nb - pos);
             float4 raw = na;
             const uint32_t my_idx = nidx;
             if (tid < C) {
@@ -326,7 +307,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 }
             }
             __syncthreads();
-            {   // intra-chunk predecessor masks: thread = (row i, 16-column group w);
+            {   // intra-round predecessor masks: thread = (row i, 16-column group w);
                 // bit j set iff j < i, both alive, and j suppresses i
                 const int i = tid >> 3, w = tid & 7;
                 unsigned int bits = 0u;
@@ -344,7 +325,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
             }
             __syncthreads();
             if (warp == 0) {
-                // Resolve the chunk in parallel rounds (same result as the sequential greedy sweep):
+                // Resolve the round in parallel sweeps (same result as the sequential greedy loop):
                 // an undecided candidate is REMOVED if a kept predecessor suppresses it, KEPT if no
                 // undecided predecessor suppresses it, else stays undecided.  Lane l owns candidates
                 // l, 32+l, 64+l, 96+l, so ballot word q is exactly bits [32q, 32q+32).
@@ -364,17 +345,15 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                         const bool und = (U[q] >> lane) & 1u;
                         const unsigned hitK = (pr[q].x & Kp[0]) | (pr[q].y & Kp[1]) | (pr[q].z & Kp[2]) | (pr[q].w & Kp[3]);
                         const unsigned hitU = (pr[q].x & U[0]) | (pr[q].y & U[1]) | (pr[q].z & U[2]) | (pr[q].w & U[3]);
-                        const bool keep = und && hitK == 0u && hitU == 0u;
-                        const bool stay = und && hitK == 0u && hitU != 0u;
-                        nK[q] = __ballot_sync(0xffffffffu, keep);
-                        nU[q] = __ballot_sync(0xffffffffu, stay);
+                        nK[q] = __ballot_sync(0xffffffffu, und && hitK == 0u && hitU == 0u);
+                        nU[q] = __ballot_sync(0xffffffffu, und && hitK == 0u && hitU != 0u);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { Kp[q] |= nK[q]; U[q] = nU[q]; }
                 }
                 // kept candidates take consecutive output slots in score order, capped at max_out
                 const int allowed = p.max_out - nkept;
-                int before = 0, total = 0;
+                int before = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int rank = before + __popc(Kp[q] & ((1u << lane) - 1u));
@@ -382,8 +361,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                     slot[q * 32 + lane] = kept ? nkept + rank : -1;
                     before += __popc(Kp[q]);
                 }
-                total = before;
-                if (lane == 0) sh.nk = min(total, allowed);
+                if (lane == 0) sh.nk = min(before, allowed);
             }
             __syncthreads();
             if (tid < C && slot[tid] >= 0) {
@@ -398,6 +376,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
             nkept += sh.nk;
             __syncthreads();
         }
+        if (nkept >= p.max_out) break;
     }
     if (p.mode == MODE_TOPK) return;
     // zero padding (TF pads boxes/scores/classes with 0); keep_idx pads with -1
@@ -425,40 +404,24 @@ static IouThreshold make_threshold(float thr) {
     return t;
 }
 
-static size_t prop_smem_bytes(int kcap, int max_out) {
+static size_t prop_smem_bytes(int n_staged, int max_out) {
     max_out = (max_out + 3) & ~3;
-    size_t s = (size_t)kcap * 16;                 // keyA, idxA, keyB, idxB
-    s += (size_t)CNT_WORDS * 4;                   // cnt
+    size_t s = (size_t)2 * BATCH * 8;               // sortbuf (double buffer)
+    s += (size_t)BATCH * 4;                         // sidx
     s += (size_t)(max_out + NMS_CHUNK) * (16 + 4);  // kbox+cbox, karea+carea
-    s += (size_t)NMS_CHUNK * (4 + 4 + 16);        // alive, slot, mask16
+    s += (size_t)NMS_CHUNK * (4 + 4 + 16);          // alive, slot, mask16
+    s += (size_t)n_staged * 4;                      // staged score keys
     return s + 16;
 }
-constexpr size_t PROP_SMEM_LIMIT = 227 * 1024 - 1024;
-
-// decide the shared-memory plan; returns 0 or an error
-static int plan(PropParams& p, size_t* smem) {
-    int kcap = (p.k + 3) & ~3;
-    if (kcap < 4) kcap = 4;
-    // staging the N score keys in sort buffer B needs N <= 2*kcap; grow kcap if that still fits
-    int kcap_staged = max(kcap, ((p.N + 1) / 2 + 3) & ~3);
-    if (prop_smem_bytes(kcap_staged, p.max_out) <= PROP_SMEM_LIMIT) {
-        kcap = kcap_staged;
-        p.staged = 1;
-    } else {
-        p.staged = 0;
-    }
-    p.kcap = kcap;
-    *smem = prop_smem_bytes(kcap, p.max_out);
-    if (*smem > PROP_SMEM_LIMIT)
-        return fail(TFRPN_ERR_UNSUPPORTED, "top-k/NMS: k=%d with %d outputs needs %zu B of shared memory (> %zu); "
-                    "k <= %d is supported by the in-SM sort", p.k, p.max_out, *smem, PROP_SMEM_LIMIT, TFRPN_MAX_SORT_K);
-    return 0;
-}
+constexpr size_t PROP_SMEM_LIMIT = 227 * 1024 - 4096;   // leaves room for the static PropShared
 
 static int launch(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
-    size_t smem = 0;
     p.mo_pad = (p.max_out + 3) & ~3;
-    if (int rc = plan(p, &smem)) return rc;
+    p.staged = prop_smem_bytes(p.N, p.max_out) <= PROP_SMEM_LIMIT ? 1 : 0;
+    const size_t smem = prop_smem_bytes(p.staged ? p.N : 0, p.max_out);
+    if (smem > PROP_SMEM_LIMIT)
+        return fail(TFRPN_ERR_UNSUPPORTED, "NMS: %d output rows need %zu B of shared memory (> %zu)", p.max_out, smem,
+                    PROP_SMEM_LIMIT);
     static thread_local bool attr_set = false;
     if (!attr_set) {
         TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROP_SMEM_LIMIT));
