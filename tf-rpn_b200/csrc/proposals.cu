@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     float* carea = karea + p.mo_pad;                                              // [NMS_CHUNK]
     unsigned int* alive = reinterpret_cast<unsigned int*>(carea + NMS_CHUNK);     // [NMS_CHUNK]
     int* slot = reinterpret_cast<int*>(alive + NMS_CHUNK);                        // [NMS_CHUNK]
-    unsigned short* mask16 = reinterpret_cast<unsigned short*>(slot + NMS_CHUNK); // [NMS_CHUNK][8]
-    uint32_t* skeys = reinterpret_cast<uint32_t*>(mask16 + NMS_CHUNK * 8);        // [N] when staged
+    unsigned int* mask32 = reinterpret_cast<unsigned int*>(slot + NMS_CHUNK);       // [NMS_CHUNK][4]
+    uint32_t* skeys = mask32 + NMS_CHUNK * 4;                                     // [N] when staged
 
     // ---- phase 0: stage keys, count entries above the score threshold ---------------------------
     unsigned int my_valid = 0;
@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 carea[tid] = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
                 alive[tid] = 1u;
             }
+            if (tid < NMS_CHUNK * 4) mask32[tid] = 0u;
             __syncthreads();
             fetch(pos + NMS_CHUNK, na, nd, nidx);   // in flight during the tests below
             {   // candidates vs kept list: thread = (candidate c, part), kept j strided by NMS_PARTS
@@ -307,21 +308,18 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 }
             }
             __syncthreads();
-            {   // intra-round predecessor masks: thread = (row i, 16-column group w);
-                // bit j set iff j < i, both alive, and j suppresses i
-                const int i = tid >> 3, w = tid & 7;
-                unsigned int bits = 0u;
-                if (i < C && alive[i] && w * 16 < i) {
-                    const float4 bi = cbox[i];
-                    const float ai = carea[i];
-                    const int jend = min(16, i - w * 16);
-#pragma unroll 4
-                    for (int jj = 0; jj < jend; ++jj) {
-                        const int j = w * 16 + jj;
-                        if (alive[j] && nms_suppresses(cbox[j], carea[j], bi, ai, thr)) bits |= 1u << jj;
-                    }
+            {   // intra-round predecessor masks: bit j of row i set iff j < i, both alive, j suppresses i.
+                // The triangle is folded so that every 16-thread team gets the same number of pairs:
+                // team r takes row iA = r + 1 (iA pairs) and row iB = C - 1 - r (iB pairs).
+                const int r = tid >> 4, sub = tid & 15;
+                const int iA = r + 1, iB = C - 1 - r;
+                const int len = (iA < iB) ? iA + iB : (iA == iB ? iA : 0);
+                for (int e = sub; e < len; e += 16) {
+                    const int i = e < iA ? iA : iB;
+                    const int j = e < iA ? e : e - iA;
+                    if (alive[i] && alive[j] && nms_suppresses(cbox[j], carea[j], cbox[i], carea[i], thr))
+                        atomicOr(&mask32[i * 4 + (j >> 5)], 1u << (j & 31));
                 }
-                mask16[i * 8 + w] = (unsigned short)bits;
             }
             __syncthreads();
             if (warp == 0) {
@@ -329,7 +327,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 // an undecided candidate is REMOVED if a kept predecessor suppresses it, KEPT if no
                 // undecided predecessor suppresses it, else stays undecided.  Lane l owns candidates
                 // l, 32+l, 64+l, 96+l, so ballot word q is exactly bits [32q, 32q+32).
-                const uint4* m4 = reinterpret_cast<const uint4*>(mask16);
+                const uint4* m4 = reinterpret_cast<const uint4*>(mask32);
                 uint4 pr[4];
                 unsigned U[4], Kp[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -398,6 +396,8 @@ static IouThreshold make_threshold(float thr) {
     t.fast = (thr >= 1e-30f && thr <= 1e30f) ? 1 : 0;
     const float nxt = nextafterf(thr, INFINITY);
     t.mid = ((double)thr + (double)nxt) * 0.5;   // exact: 25 significant bits
+    t.lo_f = (float)((double)thr * (1.0 - 1.0 / 4096.0));
+    t.hi_f = (float)((double)thr * (1.0 + 1.0 / 4096.0));
     uint32_t nb;
     memcpy(&nb, &nxt, 4);
     t.tie_up = ((nb & 1u) == 0u) ? 1 : 0;        // a tie rounds to the even mantissa
