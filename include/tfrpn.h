@@ -33,7 +33,6 @@ extern "C" {
 
 #define TFRPN_VERSION 100 /* 0.1.0 */
 #define TFRPN_MAX_BASE_ANCHORS 64
-#define TFRPN_MAX_SORT_K 11264 /* largest per-image top-k / NMS candidate count the in-SM sort holds (300 outputs) */
 
 typedef enum {
     TFRPN_OK = 0,
@@ -189,6 +188,14 @@ TFRPN_API int tfrpn_proposals_host(tfrpn_handle h, const float* rpn_reg_host, co
                          const tfrpn_proposal_cfg* cfg, float* out_boxes_host,
                          float* out_scores_host, int32_t* valid_host, int32_t* keep_idx_host_or_null,
                          tfrpn_stream s);
+/* One step from host buffers, both halves at once: the proposal half runs on an internal stream so its
+ * large H2D overlaps the target half's large D2H (full-duplex PCIe).  Same results as the two calls. */
+TFRPN_API int tfrpn_rpn_step_host(tfrpn_handle h, const float* anchors_dev,
+                        const float* gt_boxes_host, const int32_t* gt_labels_host, int B, int N, int G,
+                        const tfrpn_target_cfg* tcfg, float* deltas_host, float* labels_host,
+                        const float* rpn_reg_host, const float* rpn_cls_host, const tfrpn_proposal_cfg* pcfg,
+                        float* out_boxes_host, float* out_scores_host, int32_t* valid_host,
+                        int32_t* keep_idx_host_or_null, tfrpn_stream s);
 /* page-locked host memory for the caller's batches (so H2D/D2H run at full PCIe rate) */
 TFRPN_API int tfrpn_host_alloc(void** out, size_t bytes);
 TFRPN_API int tfrpn_host_free(void* p);

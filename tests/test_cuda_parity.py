@@ -455,3 +455,38 @@ def test_c_abi_host_entry_points(T):
                                         vp(ov), vp(ok), None))
     wb, ws, wv, wk = O.generate_proposals(reg, cls, anchors_np, hp)
     assert np.array_equal(ov, wv) and np.array_equal(ok, wk) and bits_equal(os_, ws) and close(ob, wb)
+
+
+def test_c_abi_fused_host_step_equals_separate_calls(T):
+    """tfrpn_rpn_step_host (both halves, two streams, duplex copies) == the two host calls."""
+    import ctypes as C
+    from tfrpn import _lib, synthetic
+    from tfrpn.proposals import proposal_cfg
+    from tfrpn.utils.train_utils import _target_cfg
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors_np = O.generate_anchors(hp)
+    anchors = T.cu(anchors_np)
+    B, G, N, P = 6, 17, 8649, 300
+    gtb, gtl = synthetic.gt_batch(np.random.default_rng(31), B, G)
+    reg, cls = synthetic.head_outputs(np.random.default_rng(32), B, 31, 31, 9)
+    lib, h = _lib.load(), _lib.handle(T.dev.index)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    tc, pc = _target_cfg(hp, 8, 9, 0), proposal_cfg(hp)
+    outs = []
+    for fused in (False, True, True):
+        d = np.empty((B, N, 4), F32); l = np.empty((B, N), F32)
+        ob = np.empty((B, P, 4), F32); os_ = np.empty((B, P), F32)
+        ov = np.empty((B,), np.int32); ok = np.empty((B, P), np.int32)
+        if fused:
+            _lib.check(lib.tfrpn_rpn_step_host(h, anchors.data_ptr(), vp(gtb), vp(gtl), B, N, G, C.byref(tc), vp(d), vp(l),
+                                               vp(reg), vp(cls), C.byref(pc), vp(ob), vp(os_), vp(ov), vp(ok), None))
+        else:
+            _lib.check(lib.tfrpn_rpn_targets_host(h, anchors.data_ptr(), vp(gtb), vp(gtl), B, N, G, C.byref(tc), vp(d), vp(l), None))
+            _lib.check(lib.tfrpn_proposals_host(h, vp(reg), vp(cls), anchors.data_ptr(), B, N, C.byref(pc), vp(ob), vp(os_),
+                                                vp(ov), vp(ok), None))
+        outs.append((d, l, ob, os_, ov, ok))
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+    od, ol = O.calculate_rpn_actual_outputs(anchors_np, gtb, gtl, hp, seed=8, offset=9)
+    assert bits_equal(outs[1][1], ol.reshape(B, N)) and close(outs[1][0], od)

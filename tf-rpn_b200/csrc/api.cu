@@ -16,6 +16,12 @@ struct tfrpn_ctx {
     size_t dev_bytes = 0;
     char* pinned = nullptr;   // page-locked host staging
     size_t pinned_bytes = 0;
+    char* dev2 = nullptr;     // second staging pair: the proposal half of tfrpn_rpn_step_host
+    size_t dev2_bytes = 0;
+    char* pinned2 = nullptr;
+    size_t pinned2_bytes = 0;
+    cudaStream_t side = nullptr;   // internal stream of the fused host step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool prof_on = false;
     struct Rec { cudaEvent_t a, b; int id; };
     std::vector<Rec> recs;
@@ -152,6 +158,11 @@ extern "C" int tfrpn_destroy(tfrpn_handle h) {
     if (h->ws) cudaFree(h->ws);
     if (h->dev) cudaFree(h->dev);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->dev2) cudaFree(h->dev2);
+    if (h->pinned2) cudaFreeHost(h->pinned2);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return 0;
 }
@@ -178,18 +189,102 @@ extern "C" int tfrpn_host_free(void* p) {
     return 0;
 }
 
-// copy from a caller's host buffer: directly when it is page-locked, else through pinned staging
-static int h2d(tfrpn_handle h, void* dst, const void* src, size_t bytes, char** pin_cursor, cudaStream_t s) {
+// ---- host-buffer entry points ---------------------------------------------------------------------
+// Each half has its own device + pinned staging region so that the fused step can run both at once.
+struct Staging {
+    char** dev; size_t* dev_bytes; char** pin; size_t* pin_bytes;
+};
+struct HostJob {   // copies out of pinned staging, to run after the stream has been synchronised
+    struct Copy { void* dst; const void* src; size_t bytes; } copies[8];
+    int n = 0;
+    void add(void* d, const void* s, size_t b) { copies[n].dst = d; copies[n].src = s; copies[n].bytes = b; ++n; }
+    void finish() { for (int i = 0; i < n; ++i) memcpy(copies[i].dst, copies[i].src, copies[i].bytes); n = 0; }
+};
+
+static bool is_pinned(const void* p) {
     cudaPointerAttributes attr;
-    bool is_pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    bool r = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    if (!is_pinned) {
-        memcpy(*pin_cursor, src, bytes);
-        src = *pin_cursor;
-        *pin_cursor += align256(bytes);
+    return r;
+}
+
+// copy from a caller's host buffer: directly when it is page-locked, else through pinned staging
+static int h2d(void* dst, const void* src, size_t bytes, char* pin_slot, cudaStream_t s) {
+    if (!is_pinned(src)) {
+        memcpy(pin_slot, src, bytes);
+        src = pin_slot;
     }
-    (void)h;
     TFRPN_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+// copy to a caller's host buffer: directly when it is page-locked, else staging + deferred memcpy
+static int d2h(void* dst, const void* src_dev, size_t bytes, char* pin_slot, cudaStream_t s, HostJob& job) {
+    if (is_pinned(dst)) {
+        TFRPN_CHECK_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, s));
+    } else {
+        TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin_slot, src_dev, bytes, cudaMemcpyDeviceToHost, s));
+        job.add(dst, pin_slot, bytes);
+    }
+    return 0;
+}
+
+static int targets_host_enqueue(tfrpn_handle h, const float* anchors_dev, const float* gt_boxes_host,
+                                const int32_t* gt_labels_host, int B, int N, int G, const tfrpn_target_cfg* cfg,
+                                float* deltas_host, float* labels_host, cudaStream_t st, HostJob& job) {
+    if (!gt_boxes_host || !gt_labels_host || !deltas_host || !labels_host)
+        return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: null pointer");
+    if (B <= 0 || N <= 0 || G <= 0) return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: bad shape");
+    const size_t b_gt = align256((size_t)B * G * 16), b_gl = align256((size_t)B * G * 4);
+    const size_t b_d = align256((size_t)B * N * 16), b_l = align256((size_t)B * N * 4);
+    if (int rc = grow(&h->dev, &h->dev_bytes, b_gt + b_gl + b_d + b_l, st, false)) return rc;
+    if (int rc = grow(&h->pinned, &h->pinned_bytes, b_gt + b_gl + b_d + b_l, st, true)) return rc;
+    char* d = h->dev;
+    char* pin = h->pinned;
+    float* d_gt = reinterpret_cast<float*>(d);
+    int32_t* d_gl = reinterpret_cast<int32_t*>(d + b_gt);
+    float* d_d = reinterpret_cast<float*>(d + b_gt + b_gl);
+    float* d_l = reinterpret_cast<float*>(d + b_gt + b_gl + b_d);
+    if (int rc = h2d(d_gt, gt_boxes_host, (size_t)B * G * 16, pin, st)) return rc;
+    if (int rc = h2d(d_gl, gt_labels_host, (size_t)B * G * 4, pin + b_gt, st)) return rc;
+    if (int rc = tfrpn_rpn_targets(h, anchors_dev, d_gt, d_gl, B, N, G, cfg, d_d, d_l, nullptr, st)) return rc;
+    if (int rc = d2h(deltas_host, d_d, (size_t)B * N * 16, pin + b_gt + b_gl, st, job)) return rc;
+    if (int rc = d2h(labels_host, d_l, (size_t)B * N * 4, pin + b_gt + b_gl + b_d, st, job)) return rc;
+    return 0;
+}
+
+static int proposals_host_enqueue(tfrpn_handle h, const float* rpn_reg_host, const float* rpn_cls_host,
+                                  const float* anchors_dev, int B, int N, const tfrpn_proposal_cfg* cfg,
+                                  float* out_boxes_host, float* out_scores_host, int32_t* valid_host,
+                                  int32_t* keep_idx_host_or_null, cudaStream_t st, HostJob& job) {
+    if (!rpn_reg_host || !rpn_cls_host || !cfg || !out_boxes_host || !out_scores_host || !valid_host)
+        return fail(TFRPN_ERR_BAD_ARG, "proposals_host: null pointer");
+    if (B <= 0 || N <= 0 || cfg->post_nms_topn <= 0) return fail(TFRPN_ERR_BAD_ARG, "proposals_host: bad shape");
+    const int P = cfg->post_nms_topn;
+    const size_t b_reg = align256((size_t)B * N * 16), b_cls = align256((size_t)B * N * 4);
+    const size_t b_ob = align256((size_t)B * P * 16), b_os = align256((size_t)B * P * 4);
+    const size_t b_v = align256((size_t)B * 4), b_k = align256((size_t)B * P * 4);
+    const size_t total = b_reg + b_cls + b_ob + b_os + b_v + b_k;
+    if (int rc = grow(&h->dev2, &h->dev2_bytes, total, st, false)) return rc;
+    if (int rc = grow(&h->pinned2, &h->pinned2_bytes, total, st, true)) return rc;
+    char* d = h->dev2;
+    char* pin = h->pinned2;
+    float* d_reg = reinterpret_cast<float*>(d);
+    float* d_cls = reinterpret_cast<float*>(d + b_reg);
+    char* d_out = d + b_reg + b_cls;  // boxes | scores | valid | keep, contiguous
+    float* d_ob = reinterpret_cast<float*>(d_out);
+    float* d_os = reinterpret_cast<float*>(d_out + b_ob);
+    int32_t* d_v = reinterpret_cast<int32_t*>(d_out + b_ob + b_os);
+    int32_t* d_k = reinterpret_cast<int32_t*>(d_out + b_ob + b_os + b_v);
+    if (int rc = h2d(d_reg, rpn_reg_host, (size_t)B * N * 16, pin, st)) return rc;
+    if (int rc = h2d(d_cls, rpn_cls_host, (size_t)B * N * 4, pin + b_reg, st)) return rc;
+    if (int rc = tfrpn_proposals(h, d_reg, d_cls, anchors_dev, B, N, cfg, d_ob, d_os, d_v, d_k, st)) return rc;
+    // the four small results come back in ONE D2H copy through pinned staging
+    char* p_out = pin + b_reg + b_cls;
+    TFRPN_CHECK_CUDA(cudaMemcpyAsync(p_out, d_out, b_ob + b_os + b_v + b_k, cudaMemcpyDeviceToHost, st));
+    job.add(out_boxes_host, p_out, (size_t)B * P * 16);
+    job.add(out_scores_host, p_out + b_ob, (size_t)B * P * 4);
+    job.add(valid_host, p_out + b_ob + b_os, (size_t)B * 4);
+    if (keep_idx_host_or_null) job.add(keep_idx_host_or_null, p_out + b_ob + b_os + b_v, (size_t)B * P * 4);
     return 0;
 }
 
@@ -197,41 +292,11 @@ extern "C" int tfrpn_rpn_targets_host(tfrpn_handle h, const float* anchors_dev, 
                                       const int32_t* gt_labels_host, int B, int N, int G, const tfrpn_target_cfg* cfg,
                                       float* deltas_host, float* labels_host, tfrpn_stream s) {
     if (!h) return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: null handle");
-    if (!gt_boxes_host || !gt_labels_host || !deltas_host || !labels_host)
-        return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: null pointer");
-    if (B <= 0 || N <= 0 || G <= 0) return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: bad shape");
-    cudaStream_t st = as_stream(s);
-    const size_t b_gt = align256((size_t)B * G * 16), b_gl = align256((size_t)B * G * 4);
-    const size_t b_d = align256((size_t)B * N * 16), b_l = align256((size_t)B * N * 4);
-    if (int rc = grow(&h->dev, &h->dev_bytes, b_gt + b_gl + b_d + b_l, st, false)) return rc;
-    if (int rc = grow(&h->pinned, &h->pinned_bytes, b_gt + b_gl + b_d + b_l, st, true)) return rc;
-    char* d = h->dev;
-    float* d_gt = reinterpret_cast<float*>(d);
-    int32_t* d_gl = reinterpret_cast<int32_t*>(d + b_gt);
-    float* d_d = reinterpret_cast<float*>(d + b_gt + b_gl);
-    float* d_l = reinterpret_cast<float*>(d + b_gt + b_gl + b_d);
-    char* pin = h->pinned;
-    if (int rc = h2d(h, d_gt, gt_boxes_host, (size_t)B * G * 16, &pin, st)) return rc;
-    if (int rc = h2d(h, d_gl, gt_labels_host, (size_t)B * G * 4, &pin, st)) return rc;
-    if (int rc = tfrpn_rpn_targets(h, anchors_dev, d_gt, d_gl, B, N, G, cfg, d_d, d_l, nullptr, s)) return rc;
-    // results: straight into the caller's buffers when they are page-locked, else via staging
-    cudaPointerAttributes attr;
-    bool out_pinned = cudaPointerGetAttributes(&attr, deltas_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-                      cudaPointerGetAttributes(&attr, labels_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (out_pinned) {
-        TFRPN_CHECK_CUDA(cudaMemcpyAsync(deltas_host, d_d, (size_t)B * N * 16, cudaMemcpyDeviceToHost, st));
-        TFRPN_CHECK_CUDA(cudaMemcpyAsync(labels_host, d_l, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
-        TFRPN_CHECK_CUDA(cudaStreamSynchronize(st));
-    } else {
-        char* p_d = h->pinned + b_gt + b_gl;
-        char* p_l = p_d + b_d;
-        TFRPN_CHECK_CUDA(cudaMemcpyAsync(p_d, d_d, (size_t)B * N * 16, cudaMemcpyDeviceToHost, st));
-        TFRPN_CHECK_CUDA(cudaMemcpyAsync(p_l, d_l, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
-        TFRPN_CHECK_CUDA(cudaStreamSynchronize(st));
-        memcpy(deltas_host, p_d, (size_t)B * N * 16);
-        memcpy(labels_host, p_l, (size_t)B * N * 4);
-    }
+    HostJob job;
+    if (int rc = targets_host_enqueue(h, anchors_dev, gt_boxes_host, gt_labels_host, B, N, G, cfg, deltas_host,
+                                      labels_host, as_stream(s), job)) return rc;
+    TFRPN_CHECK_CUDA(cudaStreamSynchronize(as_stream(s)));
+    job.finish();
     return 0;
 }
 
@@ -240,37 +305,40 @@ extern "C" int tfrpn_proposals_host(tfrpn_handle h, const float* rpn_reg_host, c
                                     float* out_boxes_host, float* out_scores_host, int32_t* valid_host,
                                     int32_t* keep_idx_host_or_null, tfrpn_stream s) {
     if (!h) return fail(TFRPN_ERR_BAD_ARG, "proposals_host: null handle");
-    if (!rpn_reg_host || !rpn_cls_host || !cfg || !out_boxes_host || !out_scores_host || !valid_host)
-        return fail(TFRPN_ERR_BAD_ARG, "proposals_host: null pointer");
-    if (B <= 0 || N <= 0 || cfg->post_nms_topn <= 0) return fail(TFRPN_ERR_BAD_ARG, "proposals_host: bad shape");
+    HostJob job;
+    if (int rc = proposals_host_enqueue(h, rpn_reg_host, rpn_cls_host, anchors_dev, B, N, cfg, out_boxes_host,
+                                        out_scores_host, valid_host, keep_idx_host_or_null, as_stream(s), job)) return rc;
+    TFRPN_CHECK_CUDA(cudaStreamSynchronize(as_stream(s)));
+    job.finish();
+    return 0;
+}
+
+// One training/inference step from host buffers: both halves at once.  The proposal half (large H2D,
+// small D2H) runs on an internal side stream, the target half (small H2D, large D2H) on the caller's
+// stream, so the two big PCIe transfers go in opposite directions at the same time (full duplex).
+extern "C" int tfrpn_rpn_step_host(tfrpn_handle h, const float* anchors_dev, const float* gt_boxes_host,
+                                   const int32_t* gt_labels_host, int B, int N, int G,
+                                   const tfrpn_target_cfg* tcfg, float* deltas_host, float* labels_host,
+                                   const float* rpn_reg_host, const float* rpn_cls_host,
+                                   const tfrpn_proposal_cfg* pcfg, float* out_boxes_host, float* out_scores_host,
+                                   int32_t* valid_host, int32_t* keep_idx_host_or_null, tfrpn_stream s) {
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "rpn_step_host: null handle");
     cudaStream_t st = as_stream(s);
-    const int P = cfg->post_nms_topn;
-    const size_t b_reg = align256((size_t)B * N * 16), b_cls = align256((size_t)B * N * 4);
-    const size_t b_ob = align256((size_t)B * P * 16), b_os = align256((size_t)B * P * 4);
-    const size_t b_v = align256((size_t)B * 4), b_k = align256((size_t)B * P * 4);
-    const size_t total = b_reg + b_cls + b_ob + b_os + b_v + b_k;
-    if (int rc = grow(&h->dev, &h->dev_bytes, total, st, false)) return rc;
-    if (int rc = grow(&h->pinned, &h->pinned_bytes, total, st, true)) return rc;
-    char* d = h->dev;
-    float* d_reg = reinterpret_cast<float*>(d);
-    float* d_cls = reinterpret_cast<float*>(d + b_reg);
-    char* d_out = d + b_reg + b_cls;  // boxes | scores | valid | keep, contiguous
-    float* d_ob = reinterpret_cast<float*>(d_out);
-    float* d_os = reinterpret_cast<float*>(d_out + b_ob);
-    int32_t* d_v = reinterpret_cast<int32_t*>(d_out + b_ob + b_os);
-    int32_t* d_k = reinterpret_cast<int32_t*>(d_out + b_ob + b_os + b_v);
-    char* pin = h->pinned;
-    if (int rc = h2d(h, d_reg, rpn_reg_host, (size_t)B * N * 16, &pin, st)) return rc;
-    if (int rc = h2d(h, d_cls, rpn_cls_host, (size_t)B * N * 4, &pin, st)) return rc;
-    if (int rc = tfrpn_proposals(h, d_reg, d_cls, anchors_dev, B, N, cfg, d_ob, d_os, d_v, d_k, s)) return rc;
-    // the four small results come back in ONE D2H copy through pinned staging
-    char* p_out = h->pinned + b_reg + b_cls;
-    const size_t out_bytes = b_ob + b_os + b_v + b_k;
-    TFRPN_CHECK_CUDA(cudaMemcpyAsync(p_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (!h->side) {
+        TFRPN_CHECK_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    HostJob job;
+    TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_fork, st));
+    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    if (int rc = proposals_host_enqueue(h, rpn_reg_host, rpn_cls_host, anchors_dev, B, N, pcfg, out_boxes_host,
+                                        out_scores_host, valid_host, keep_idx_host_or_null, h->side, job)) return rc;
+    if (int rc = targets_host_enqueue(h, anchors_dev, gt_boxes_host, gt_labels_host, B, N, G, tcfg, deltas_host,
+                                      labels_host, st, job)) return rc;
+    TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_join, h->side));
+    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     TFRPN_CHECK_CUDA(cudaStreamSynchronize(st));
-    memcpy(out_boxes_host, p_out, (size_t)B * P * 16);
-    memcpy(out_scores_host, p_out + b_ob, (size_t)B * P * 4);
-    memcpy(valid_host, p_out + b_ob + b_os, (size_t)B * 4);
-    if (keep_idx_host_or_null) memcpy(keep_idx_host_or_null, p_out + b_ob + b_os + b_v, (size_t)B * P * 4);
+    job.finish();
     return 0;
 }

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "tfrpn_proposals": (I, [P, P, P, P, I, I, C.POINTER(ProposalCfg), P, P, P, P, P]),
     "tfrpn_rpn_targets_host": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P]),
     "tfrpn_proposals_host": (I, [P, P, P, P, I, I, C.POINTER(ProposalCfg), P, P, P, P, P]),
+    "tfrpn_rpn_step_host": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P, P, C.POINTER(ProposalCfg), P, P, P, P, P]),
     "tfrpn_host_alloc": (I, [C.POINTER(P), C.c_size_t]),
     "tfrpn_host_free": (I, [P]),
 }
