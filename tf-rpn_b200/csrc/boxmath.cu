@@ -1,6 +1,7 @@
 // boxmath.cu -- anchors, IoU map, delta encode / decode, (de)normalise.
 // Replaces utils/bbox_utils.py:3-46, :72-96, :98-124, :126-150, :152-182 of the reference.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -152,10 +153,11 @@ __global__ void __launch_bounds__(EW_THREADS) encode_kernel(const float4* __rest
 
 // get_bboxes_from_deltas (utils/bbox_utils.py:72-96) with the caller-side `deltas *= variances`
 // (predictor.py:55) and the proposal pipeline's clip fused in.  K3: 32*B*N algorithmic bytes.
-template <bool SCALE, bool CLIP>
+template <bool SCALE, bool CLIP, int PT>
 __global__ void __launch_bounds__(EW_THREADS) decode_kernel(const float4* __restrict__ anchors, int anchors_batched,
                                                             const float4* __restrict__ deltas, float4 var, int N,
                                                             float4* __restrict__ out) {
+    constexpr int EW_PER_THREAD = PT;
     const long long img = (long long)blockIdx.y * N;
     const float4* an = anchors + (anchors_batched ? img : 0);
     const int n0 = blockIdx.x * (EW_THREADS * EW_PER_THREAD) + threadIdx.x;
@@ -294,12 +296,19 @@ extern "C" int tfrpn_decode(const float* anchors, int anchors_batched, const flo
     const float4* d4 = reinterpret_cast<const float4*>(deltas);
     float4* o4 = reinterpret_cast<float4*>(out);
     if (B > 65535) return fail(TFRPN_ERR_UNSUPPORTED, "decode: B > 65535");
-    dim3 grid = ew_grid2(B, N);
     cudaStream_t st = as_stream(s);
-    if (scale && clip) decode_kernel<true, true><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);
-    else if (scale) decode_kernel<true, false><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);
-    else if (clip) decode_kernel<false, true><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);
-    else decode_kernel<false, false><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);
+    static int pt = 0;
+    if (pt == 0) { const char* e = getenv("TFRPN_DECODE_PT"); pt = e ? atoi(e) : 2; if (pt != 1 && pt != 2 && pt != 4) pt = 2; }
+#define TFRPN_DECODE_LAUNCH(PT)                                                                                      \
+    do {                                                                                                             \
+        dim3 grid((N + EW_THREADS * PT - 1) / (EW_THREADS * PT), B);                                                 \
+        if (scale && clip) decode_kernel<true, true, PT><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);   \
+        else if (scale) decode_kernel<true, false, PT><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);     \
+        else if (clip) decode_kernel<false, true, PT><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);      \
+        else decode_kernel<false, false, PT><<<grid, EW_THREADS, 0, st>>>(a4, anchors_batched, d4, var, N, o4);               \
+    } while (0)
+    if (pt == 1) TFRPN_DECODE_LAUNCH(1); else if (pt == 4) TFRPN_DECODE_LAUNCH(4); else TFRPN_DECODE_LAUNCH(2);
+#undef TFRPN_DECODE_LAUNCH
     TFRPN_AFTER_LAUNCH("decode_kernel");
     return 0;
 }
