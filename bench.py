@@ -130,7 +130,8 @@ def run_reference(args):
     hp = rpn_oracle.get_hyper_params("vgg16")
     anchors = rpn_oracle.generate_anchors(hp)
     cores = os.cpu_count() or 1
-    threads = c_oracle.max_threads() if c_oracle.available() else 1
+    # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1: override it)
+    threads = len(os.sched_getaffinity(0)) if c_oracle.available() else 1
     sets = make_inputs(0, 2, B_PER_GPU)
     W, K = max(args.warmup, 1), max(args.steps, 1)
     K = min(K, 20)   # bounded: each step is a full 64-image batch on the CPU
@@ -162,6 +163,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # keep stdout clean for the ONE JSON line: libraries (NCCL prints its version) go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; tfrpn has no CPU fallback")
     torch.cuda.set_device(local)
@@ -390,18 +394,21 @@ def run_ours(args):
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle, rpn_oracle
-        threads = c_oracle.max_threads() if c_oracle.available() else 1
+        threads = len(os.sched_getaffinity(0)) if c_oracle.available() else 1
         a_np = rpn_oracle.generate_anchors(hp)
         t_cpu, n_img, what = 0.0, 0, ""
-        while t_cpu < 10.0 and n_img < 64 * 50:
+        while t_cpu < 10.0 and n_img < 64 * 2000:
             dt, what = cpu_path(np_sets, a_np, hp, threads, B)
             t_cpu += dt
             n_img += B
         line["cpu_baseline"] = {"value": n_img / t_cpu, "unit": "images/s", "cores": threads, "kind": "port",
                                 "sample": "%d images (batches of 64) in %.1f s, %s; host has %d cores"
                                           % (n_img, t_cpu, what, os.cpu_count() or 1)}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

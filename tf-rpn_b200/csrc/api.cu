@@ -20,8 +20,8 @@ struct tfrpn_ctx {
     size_t dev2_bytes = 0;
     char* pinned2 = nullptr;
     size_t pinned2_bytes = 0;
-    cudaStream_t side = nullptr;   // internal stream of the fused host step
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side = nullptr, copy_in = nullptr, copy_out = nullptr;   // internal streams of the fused host step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_a = nullptr, ev_b = nullptr;
     bool prof_on = false;
     struct Rec { cudaEvent_t a, b; int id; };
     std::vector<Rec> recs;
@@ -161,8 +161,12 @@ extern "C" int tfrpn_destroy(tfrpn_handle h) {
     if (h->dev2) cudaFree(h->dev2);
     if (h->pinned2) cudaFreeHost(h->pinned2);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
     delete h;
     return 0;
 }
@@ -195,7 +199,7 @@ struct Staging {
     char** dev; size_t* dev_bytes; char** pin; size_t* pin_bytes;
 };
 struct HostJob {   // copies out of pinned staging, to run after the stream has been synchronised
-    struct Copy { void* dst; const void* src; size_t bytes; } copies[8];
+    struct Copy { void* dst; const void* src; size_t bytes; } copies[24];
     int n = 0;
     void add(void* d, const void* s, size_t b) { copies[n].dst = d; copies[n].src = s; copies[n].bytes = b; ++n; }
     void finish() { for (int i = 0; i < n; ++i) memcpy(copies[i].dst, copies[i].src, copies[i].bytes); n = 0; }
@@ -313,9 +317,19 @@ extern "C" int tfrpn_proposals_host(tfrpn_handle h, const float* rpn_reg_host, c
     return 0;
 }
 
-// One training/inference step from host buffers: both halves at once.  The proposal half (large H2D,
-// small D2H) runs on an internal side stream, the target half (small H2D, large D2H) on the caller's
-// stream, so the two big PCIe transfers go in opposite directions at the same time (full duplex).
+// One training/inference step from host buffers: both halves at once, pipelined over image chunks.
+//   caller's stream : H2D gt (tiny) -> for each chunk: targets kernels
+//   copy-out stream : D2H deltas/labels of chunk c as soon as its kernels are done (overlaps chunk c+1)
+//   copy-in stream  : H2D rpn_reg/rpn_cls of chunk c
+//   side stream     : proposals of chunk c as soon as its inputs have landed; one small D2H at the end
+// so the two large PCIe transfers (11 MB each way at C2) run concurrently in opposite directions and
+// only ~one chunk of compute is exposed.  Results are identical to the two separate calls: the counter
+// RNG is keyed by the global image index (image_offset), and images are independent.
+static int make_stream(cudaStream_t* s) {
+    if (!*s) TFRPN_CHECK_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+    return 0;
+}
+
 extern "C" int tfrpn_rpn_step_host(tfrpn_handle h, const float* anchors_dev, const float* gt_boxes_host,
                                    const int32_t* gt_labels_host, int B, int N, int G,
                                    const tfrpn_target_cfg* tcfg, float* deltas_host, float* labels_host,
@@ -323,21 +337,92 @@ extern "C" int tfrpn_rpn_step_host(tfrpn_handle h, const float* anchors_dev, con
                                    const tfrpn_proposal_cfg* pcfg, float* out_boxes_host, float* out_scores_host,
                                    int32_t* valid_host, int32_t* keep_idx_host_or_null, tfrpn_stream s) {
     if (!h) return fail(TFRPN_ERR_BAD_ARG, "rpn_step_host: null handle");
+    if (!gt_boxes_host || !gt_labels_host || !deltas_host || !labels_host || !tcfg || !rpn_reg_host || !rpn_cls_host ||
+        !pcfg || !out_boxes_host || !out_scores_host || !valid_host)
+        return fail(TFRPN_ERR_BAD_ARG, "rpn_step_host: null pointer");
+    if (B <= 0 || N <= 0 || G <= 0 || pcfg->post_nms_topn <= 0) return fail(TFRPN_ERR_BAD_ARG, "rpn_step_host: bad shape");
     cudaStream_t st = as_stream(s);
-    if (!h->side) {
-        TFRPN_CHECK_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    if (int rc = make_stream(&h->side)) return rc;
+    if (int rc = make_stream(&h->copy_in)) return rc;
+    if (int rc = make_stream(&h->copy_out)) return rc;
+    if (!h->ev_fork) {
         TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+        TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     }
+    const int P = pcfg->post_nms_topn;
+    // staging: region 1 = target half, region 2 = proposal half
+    const size_t b_gt = align256((size_t)B * G * 16), b_gl = align256((size_t)B * G * 4);
+    const size_t b_d = align256((size_t)B * N * 16), b_l = align256((size_t)B * N * 4);
+    const size_t b_reg = align256((size_t)B * N * 16), b_cls = align256((size_t)B * N * 4);
+    const size_t b_ob = align256((size_t)B * P * 16), b_os = align256((size_t)B * P * 4);
+    const size_t b_v = align256((size_t)B * 4), b_k = align256((size_t)B * P * 4);
+    if (int rc = grow(&h->dev, &h->dev_bytes, b_gt + b_gl + b_d + b_l, st, false)) return rc;
+    if (int rc = grow(&h->pinned, &h->pinned_bytes, b_gt + b_gl + b_d + b_l, st, true)) return rc;
+    if (int rc = grow(&h->dev2, &h->dev2_bytes, b_reg + b_cls + b_ob + b_os + b_v + b_k, st, false)) return rc;
+    if (int rc = grow(&h->pinned2, &h->pinned2_bytes, b_reg + b_cls + b_ob + b_os + b_v + b_k, st, true)) return rc;
+    if (int rc = tfrpn_reserve(h, B, N, G, 0)) return rc;
+    float* d_gt = reinterpret_cast<float*>(h->dev);
+    int32_t* d_gl = reinterpret_cast<int32_t*>(h->dev + b_gt);
+    float* d_d = reinterpret_cast<float*>(h->dev + b_gt + b_gl);
+    float* d_l = reinterpret_cast<float*>(h->dev + b_gt + b_gl + b_d);
+    float* d_reg = reinterpret_cast<float*>(h->dev2);
+    float* d_cls = reinterpret_cast<float*>(h->dev2 + b_reg);
+    char* d_out = h->dev2 + b_reg + b_cls;
+    float* d_ob = reinterpret_cast<float*>(d_out);
+    float* d_os = reinterpret_cast<float*>(d_out + b_ob);
+    int32_t* d_v = reinterpret_cast<int32_t*>(d_out + b_ob + b_os);
+    int32_t* d_k = reinterpret_cast<int32_t*>(d_out + b_ob + b_os + b_v);
+    char* pin1 = h->pinned;
+    char* pin2 = h->pinned2;
+
+    const int chunks = B >= 32 ? 4 : (B >= 8 ? 2 : 1);
     HostJob job;
+    // everything below is ordered after the caller's prior work on `st`
     TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_fork, st));
+    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->copy_in, h->ev_fork, 0));
     TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    if (int rc = proposals_host_enqueue(h, rpn_reg_host, rpn_cls_host, anchors_dev, B, N, pcfg, out_boxes_host,
-                                        out_scores_host, valid_host, keep_idx_host_or_null, h->side, job)) return rc;
-    if (int rc = targets_host_enqueue(h, anchors_dev, gt_boxes_host, gt_labels_host, B, N, G, tcfg, deltas_host,
-                                      labels_host, st, job)) return rc;
+    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_fork, 0));
+    if (int rc = h2d(d_gt, gt_boxes_host, (size_t)B * G * 16, pin1, st)) return rc;
+    if (int rc = h2d(d_gl, gt_labels_host, (size_t)B * G * 4, pin1 + b_gt, st)) return rc;
+    for (int c = 0; c < chunks; ++c) {
+        const int lo = (int)((long long)B * c / chunks), hi = (int)((long long)B * (c + 1) / chunks), nb = hi - lo;
+        if (nb == 0) continue;
+        // proposal half: inputs of this chunk, then its kernel
+        if (int rc = h2d(d_reg + (size_t)lo * N * 4, rpn_reg_host + (size_t)lo * N * 4, (size_t)nb * N * 16,
+                         pin2 + (size_t)lo * N * 16, h->copy_in)) return rc;
+        if (int rc = h2d(d_cls + (size_t)lo * N, rpn_cls_host + (size_t)lo * N, (size_t)nb * N * 4,
+                         pin2 + b_reg + (size_t)lo * N * 4, h->copy_in)) return rc;
+        TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_a, h->copy_in));
+        TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->side, h->ev_a, 0));
+        if (int rc = tfrpn_proposals(h, d_reg + (size_t)lo * N * 4, d_cls + (size_t)lo * N, anchors_dev, nb, N, pcfg,
+                                     d_ob + (size_t)lo * P * 4, d_os + (size_t)lo * P, d_v + lo, d_k + (size_t)lo * P,
+                                     h->side)) return rc;
+        // target half: kernels of this chunk, then its results go home while the next chunk computes
+        tfrpn_target_cfg cc = *tcfg;
+        cc.image_offset = tcfg->image_offset + lo;
+        if (int rc = tfrpn_rpn_targets(h, anchors_dev, d_gt + (size_t)lo * G * 4, d_gl + (size_t)lo * G, nb, N, G, &cc,
+                                       d_d + (size_t)lo * N * 4, d_l + (size_t)lo * N, nullptr, st)) return rc;
+        TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_b, st));
+        TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_b, 0));
+        if (int rc = d2h(deltas_host + (size_t)lo * N * 4, d_d + (size_t)lo * N * 4, (size_t)nb * N * 16,
+                         pin1 + b_gt + b_gl + (size_t)lo * N * 16, h->copy_out, job)) return rc;
+        if (int rc = d2h(labels_host + (size_t)lo * N, d_l + (size_t)lo * N, (size_t)nb * N * 4,
+                         pin1 + b_gt + b_gl + b_d + (size_t)lo * N * 4, h->copy_out, job)) return rc;
+    }
+    // the four small proposal results come back in ONE D2H copy through pinned staging
+    char* p_out = pin2 + b_reg + b_cls;
+    TFRPN_CHECK_CUDA(cudaMemcpyAsync(p_out, d_out, b_ob + b_os + b_v + b_k, cudaMemcpyDeviceToHost, h->side));
+    job.add(out_boxes_host, p_out, (size_t)B * P * 16);
+    job.add(out_scores_host, p_out + b_ob, (size_t)B * P * 4);
+    job.add(valid_host, p_out + b_ob + b_os, (size_t)B * 4);
+    if (keep_idx_host_or_null) job.add(keep_idx_host_or_null, p_out + b_ob + b_os + b_v, (size_t)B * P * 4);
+    // join everything back into the caller's stream
     TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_join, h->side));
     TFRPN_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_a, h->copy_out));
+    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_a, 0));
     TFRPN_CHECK_CUDA(cudaStreamSynchronize(st));
     job.finish();
     return 0;
