@@ -196,6 +196,49 @@ TFRPN_API int tfrpn_rpn_step_host(tfrpn_handle h, const float* anchors_dev,
                         const float* rpn_reg_host, const float* rpn_cls_host, const tfrpn_proposal_cfg* pcfg,
                         float* out_boxes_host, float* out_scores_host, int32_t* valid_host,
                         int32_t* keep_idx_host_or_null, tfrpn_stream s);
+/* ---- pipelined host steps: the generator call site (utils/train_utils.py:67-82, driven by Keras
+ *      from trainer.py:48-49,64-69) and the predictor loop (predictor.py:48-60).  A step is PCIe-bound
+ *      (~11 MB each way at C2), so `depth` steps are kept in flight: the H2D of step i+1 runs under
+ *      the D2H of step i on the pipeline's own streams.  submit() only enqueues and returns a ticket;
+ *      wait() returns when that step's results are in the caller's host buffers (tickets complete in
+ *      order; submitting into a slot that is still busy retires its old step first).  Either half may
+ *      be skipped: gt_boxes_host == NULL -> no target assignment, rpn_reg_host == NULL -> no
+ *      proposals.  Host buffers must stay valid until wait(); page-locked ones (tfrpn_host_alloc) are
+ *      copied directly, others through the slot's pinned staging.  While steps are in flight the
+ *      handle's workspace belongs to the pipeline: do not call tfrpn_rpn_targets on it concurrently. */
+typedef struct tfrpn_pipe* tfrpn_pipeline;
+TFRPN_API int tfrpn_pipeline_create(tfrpn_handle h, int depth /* 1..8 */, tfrpn_pipeline* out);
+TFRPN_API int tfrpn_pipeline_submit(tfrpn_pipeline p, const float* anchors_dev /* (N,4) device */, int B, int N,
+                          const float* gt_boxes_host, const int32_t* gt_labels_host, int G,
+                          const tfrpn_target_cfg* tcfg, float* deltas_host, float* labels_host,
+                          const float* rpn_reg_host, const float* rpn_cls_host, const tfrpn_proposal_cfg* pcfg,
+                          float* out_boxes_host, float* out_scores_host, int32_t* valid_host,
+                          int32_t* keep_idx_host_or_null, int64_t* ticket_out);
+/* Zero-copy variant: borrow the next slot's page-locked step buffers, fill the inputs in place (the
+ * data loader writes its padded batch / the head outputs straight into them), submit, and after
+ * wait() read the results in place.  Inputs are one contiguous block and results another, so a step
+ * is exactly ONE H2D and ONE D2H copy -- the pattern that reaches the link's duplex rate.  The
+ * pointers stay valid until the slot is acquired again (depth steps later).  tcfg / pcfg NULL skips
+ * that half. */
+typedef struct {
+    float* gt_boxes;    /* (B,G,4)  in  */
+    int32_t* gt_labels; /* (B,G)    in  */
+    float* rpn_reg;     /* (B,N,4)  in  */
+    float* rpn_cls;     /* (B,N)    in  */
+    float* deltas;      /* (B,N,4)  out */
+    float* labels;      /* (B,N)    out */
+    float* out_boxes;   /* (B,post,4) out */
+    float* out_scores;  /* (B,post) out */
+    int32_t* valid;     /* (B,)     out */
+    int32_t* keep_idx;  /* (B,post) out */
+} tfrpn_step_buffers;
+TFRPN_API int tfrpn_pipeline_acquire(tfrpn_pipeline p, int B, int N, int G, int post_nms_topn, tfrpn_step_buffers* out);
+TFRPN_API int tfrpn_pipeline_submit_acquired(tfrpn_pipeline p, const float* anchors_dev,
+                                   const tfrpn_target_cfg* tcfg_or_null, const tfrpn_proposal_cfg* pcfg_or_null,
+                                   int64_t* ticket_out);
+TFRPN_API int tfrpn_pipeline_wait(tfrpn_pipeline p, int64_t ticket);
+TFRPN_API int tfrpn_pipeline_drain(tfrpn_pipeline p); /* wait for every step in flight */
+TFRPN_API int tfrpn_pipeline_destroy(tfrpn_pipeline p);
 /* page-locked host memory for the caller's batches (so H2D/D2H run at full PCIe rate) */
 TFRPN_API int tfrpn_host_alloc(void** out, size_t bytes);
 TFRPN_API int tfrpn_host_free(void* p);

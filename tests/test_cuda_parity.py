@@ -490,3 +490,142 @@ def test_c_abi_fused_host_step_equals_separate_calls(T):
             assert np.array_equal(a, b)
     od, ol = O.calculate_rpn_actual_outputs(anchors_np, gtb, gtl, hp, seed=8, offset=9)
     assert bits_equal(outs[1][1], ol.reshape(B, N)) and close(outs[1][0], od)
+
+
+def test_c_abi_pipeline_in_flight_steps_equal_oracle(T):
+    """tfrpn_pipeline_*: several host steps in flight (slots reused), pinned and pageable buffers,
+    both halves / targets only / proposals only -- every step equals the oracle."""
+    import ctypes as C
+    from tfrpn import _lib, synthetic
+    from tfrpn.proposals import proposal_cfg
+    from tfrpn.utils.train_utils import _target_cfg
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors_np = O.generate_anchors(hp)
+    anchors = T.cu(anchors_np)
+    B, G, N, P = 9, 11, 8649, 300
+    lib, h = _lib.load(), _lib.handle(T.dev.index)
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    pipe = C.c_void_p()
+    _lib.check(lib.tfrpn_pipeline_create(h, 2, C.byref(pipe)))
+    pinned_ptrs = []
+
+    def buf(shape, dtype, pinned):
+        if not pinned:
+            return np.empty(shape, dtype)
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _lib.check(lib.tfrpn_host_alloc(C.byref(p), n))
+        pinned_ptrs.append(p)
+        return np.frombuffer((C.c_char * n).from_address(p.value), dtype=dtype).reshape(shape)
+
+    pc = proposal_cfg(hp)
+    steps = []
+    try:
+        for i in range(5):
+            pinned = i % 2 == 0
+            mode = ("both", "targets", "proposals", "both", "both")[i]
+            gtb0, gtl0 = synthetic.gt_batch(np.random.default_rng(100 + i), B, G)
+            reg0, cls0 = synthetic.head_outputs(np.random.default_rng(200 + i), B, 31, 31, 9)
+            st = dict(mode=mode, tc=_target_cfg(hp, 3, i, 7 * i))
+            for k, (a, dt) in dict(gtb=(gtb0, F32), gtl=(gtl0, np.int32), reg=(reg0, F32), cls=(cls0, F32)).items():
+                st[k] = buf(a.shape, dt, pinned)
+                st[k][...] = a
+            for k, (sh, dt) in dict(d=((B, N, 4), F32), l=((B, N), F32), ob=((B, P, 4), F32), os=((B, P), F32),
+                                    ov=((B,), np.int32), ok=((B, P), np.int32)).items():
+                st[k] = buf(sh, dt, pinned)
+                st[k][...] = 77
+            t_on, p_on = mode != "proposals", mode != "targets"
+            ticket = C.c_int64(-1)
+            _lib.check(lib.tfrpn_pipeline_submit(
+                pipe, anchors.data_ptr(), B, N,
+                vp(st["gtb"]) if t_on else None, vp(st["gtl"]) if t_on else None, G, C.byref(st["tc"]),
+                vp(st["d"]) if t_on else None, vp(st["l"]) if t_on else None,
+                vp(st["reg"]) if p_on else None, vp(st["cls"]) if p_on else None, C.byref(pc),
+                vp(st["ob"]), vp(st["os"]), vp(st["ov"]), vp(st["ok"]), C.byref(ticket)))
+            assert ticket.value == i
+            st["ticket"] = ticket.value
+            steps.append(st)
+        _lib.check(lib.tfrpn_pipeline_wait(pipe, 4))        # out of order: 4 first, then the rest (already retired or not)
+        for st in steps:
+            _lib.check(lib.tfrpn_pipeline_wait(pipe, st["ticket"]))
+        assert lib.tfrpn_pipeline_wait(pipe, 99) == -1
+        _lib.check(lib.tfrpn_pipeline_drain(pipe))
+        for i, st in enumerate(steps):
+            if st["mode"] != "proposals":
+                od, ol = O.calculate_rpn_actual_outputs(anchors_np, st["gtb"], st["gtl"], hp, seed=3, offset=i, image_offset=7 * i)
+                assert bits_equal(st["l"], ol.reshape(B, N)) and close(st["d"], od)
+            else:
+                assert np.all(st["l"] == 77)
+            if st["mode"] != "targets":
+                wb, ws, wv, wk = O.generate_proposals(st["reg"], st["cls"], anchors_np, hp)
+                assert np.array_equal(st["ov"], wv) and np.array_equal(st["ok"], wk)
+                assert bits_equal(st["os"], ws) and close(st["ob"], wb)
+            else:
+                assert np.all(st["ov"] == 77)
+    finally:
+        _lib.check(lib.tfrpn_pipeline_destroy(pipe))
+        for p in pinned_ptrs:
+            lib.tfrpn_host_free(p)
+
+
+def test_host_pipeline_acquired_slots_equal_oracle(T):
+    """tfrpn.HostPipeline (tfrpn_pipeline_acquire / submit_acquired): inputs written into the slot's pinned
+    block, one copy per direction, three steps in flight, changing batch shape -- every step equals the oracle."""
+    from tfrpn import HostPipeline, synthetic
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors_np = O.generate_anchors(hp)
+    pipe = HostPipeline(hp, depth=3)
+    N = pipe.N
+    pending, checked = [], 0
+
+    def check(item):
+        t, v, mode, i, gtb, gtl, reg, cls = item
+        pipe.wait(t)
+        B = gtb.shape[0]
+        if mode != "proposals":
+            od, ol = O.calculate_rpn_actual_outputs(anchors_np, gtb, gtl, hp, seed=11, offset=i, image_offset=3 * i)
+            assert bits_equal(v.labels, ol) and close(v.deltas, od)
+        if mode != "targets":
+            wb, ws, wv, wk = O.generate_proposals(reg, cls, anchors_np, hp)
+            assert np.array_equal(v.valid, wv) and np.array_equal(v.keep_idx, wk)
+            assert bits_equal(v.out_scores, ws) and close(v.out_boxes, wb)
+
+    try:
+        for i in range(8):
+            B, G = (5, 9) if i < 5 else (7, 21)       # the slot staging regrows at step 5
+            mode = ("both", "targets", "proposals", "both")[i % 4]
+            gtb, gtl = synthetic.gt_batch(np.random.default_rng(300 + i), B, G)
+            reg, cls = synthetic.head_outputs(np.random.default_rng(400 + i), B, 31, 31, 9)
+            if len(pending) == 3:
+                check(pending.pop(0)); checked += 1
+            v = pipe.acquire(B, G)
+            assert v.deltas.shape == (B, N, 4) and v.labels.shape == (B, 31, 31, 9)
+            v.gt_boxes[...] = gtb; v.gt_labels[...] = gtl; v.rpn_reg[...] = reg; v.rpn_cls[...] = cls
+            t = pipe.submit(targets=mode != "proposals", proposals=mode != "targets", seed=11, offset=i, image_offset=3 * i)
+            pending.append((t, v, mode, i, gtb, gtl, reg, cls))
+        while pending:
+            check(pending.pop(0)); checked += 1
+        assert checked == 8
+    finally:
+        pipe.close()
+
+
+def test_prefetching_rpn_generator_matches_reference_generator(T):
+    """train_utils.rpn_generator(prefetch=2) (utils/train_utils.py:67-82 with steps in flight) yields the
+    same (img, (deltas, labels)) sequence as the oracle computes batch by batch, and cycles forever."""
+    from tfrpn import synthetic
+    hp = dict(O.get_hyper_params("vgg16"), seed=5)
+    anchors_np = O.generate_anchors(hp)
+    anchors = T.cu(anchors_np)
+    data = []
+    for i in range(3):
+        gtb, gtl = synthetic.gt_batch(np.random.default_rng(500 + i), 4, 12)
+        data.append(("img%d" % i, gtb, gtl))
+    gen = T.train.rpn_generator(data, anchors, hp, prefetch=2)
+    for step in range(7):                      # more than two epochs of the 3-batch dataset
+        img, (deltas, labels) = next(gen)
+        name, gtb, gtl = data[step % 3]
+        assert img == name
+        od, ol = O.calculate_rpn_actual_outputs(anchors_np, gtb, gtl, hp, seed=5, offset=step)
+        assert bits_equal(labels, ol) and close(deltas, od)
+    gen.close()

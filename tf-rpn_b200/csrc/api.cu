@@ -7,26 +7,6 @@
 
 #include "common.cuh"
 
-struct tfrpn_ctx {
-    int device = 0;
-    int sm_count = 148;
-    char* ws = nullptr;       // device workspace (kernels' scratch)
-    size_t ws_bytes = 0;
-    char* dev = nullptr;      // device staging for the *_host entry points
-    size_t dev_bytes = 0;
-    char* pinned = nullptr;   // page-locked host staging
-    size_t pinned_bytes = 0;
-    char* dev2 = nullptr;     // second staging pair: the proposal half of tfrpn_rpn_step_host
-    size_t dev2_bytes = 0;
-    char* pinned2 = nullptr;
-    size_t pinned2_bytes = 0;
-    cudaStream_t side = nullptr, copy_in = nullptr, copy_out = nullptr;   // internal streams of the fused host step
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_a = nullptr, ev_b = nullptr;
-    bool prof_on = false;
-    struct Rec { cudaEvent_t a, b; int id; };
-    std::vector<Rec> recs;
-};
-
 namespace tfrpn {
 
 static thread_local char g_err[512] = "";
@@ -50,7 +30,7 @@ size_t targets_workspace_bytes(int B, int N, int G);  // targets.cu
 
 int sm_count_of(tfrpn_handle h) { return h ? h->sm_count : 148; }
 
-static int grow(char** buf, size_t* have, size_t want, cudaStream_t s, bool pinned) {
+int grow_buffer(char** buf, size_t* have, size_t want, cudaStream_t s, bool pinned) {
     if (want <= *have) return 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
@@ -71,7 +51,7 @@ static int grow(char** buf, size_t* have, size_t want, cudaStream_t s, bool pinn
 }
 
 int ensure_workspace(tfrpn_handle h, size_t bytes, cudaStream_t s, char** out) {
-    if (int rc = grow(&h->ws, &h->ws_bytes, bytes, s, false)) return rc;
+    if (int rc = grow_buffer(&h->ws, &h->ws_bytes, bytes, s, false)) return rc;
     *out = h->ws;
     return 0;
 }
@@ -160,13 +140,7 @@ extern "C" int tfrpn_destroy(tfrpn_handle h) {
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->dev2) cudaFree(h->dev2);
     if (h->pinned2) cudaFreeHost(h->pinned2);
-    if (h->side) cudaStreamDestroy(h->side);
-    if (h->copy_in) cudaStreamDestroy(h->copy_in);
-    if (h->copy_out) cudaStreamDestroy(h->copy_out);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->ev_a) cudaEventDestroy(h->ev_a);
-    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    if (h->step_pipe) pipe_destroy(h->step_pipe);
     delete h;
     return 0;
 }
@@ -240,8 +214,8 @@ static int targets_host_enqueue(tfrpn_handle h, const float* anchors_dev, const 
     if (B <= 0 || N <= 0 || G <= 0) return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: bad shape");
     const size_t b_gt = align256((size_t)B * G * 16), b_gl = align256((size_t)B * G * 4);
     const size_t b_d = align256((size_t)B * N * 16), b_l = align256((size_t)B * N * 4);
-    if (int rc = grow(&h->dev, &h->dev_bytes, b_gt + b_gl + b_d + b_l, st, false)) return rc;
-    if (int rc = grow(&h->pinned, &h->pinned_bytes, b_gt + b_gl + b_d + b_l, st, true)) return rc;
+    if (int rc = grow_buffer(&h->dev, &h->dev_bytes, b_gt + b_gl + b_d + b_l, st, false)) return rc;
+    if (int rc = grow_buffer(&h->pinned, &h->pinned_bytes, b_gt + b_gl + b_d + b_l, st, true)) return rc;
     char* d = h->dev;
     char* pin = h->pinned;
     float* d_gt = reinterpret_cast<float*>(d);
@@ -268,8 +242,8 @@ static int proposals_host_enqueue(tfrpn_handle h, const float* rpn_reg_host, con
     const size_t b_ob = align256((size_t)B * P * 16), b_os = align256((size_t)B * P * 4);
     const size_t b_v = align256((size_t)B * 4), b_k = align256((size_t)B * P * 4);
     const size_t total = b_reg + b_cls + b_ob + b_os + b_v + b_k;
-    if (int rc = grow(&h->dev2, &h->dev2_bytes, total, st, false)) return rc;
-    if (int rc = grow(&h->pinned2, &h->pinned2_bytes, total, st, true)) return rc;
+    if (int rc = grow_buffer(&h->dev2, &h->dev2_bytes, total, st, false)) return rc;
+    if (int rc = grow_buffer(&h->pinned2, &h->pinned2_bytes, total, st, true)) return rc;
     char* d = h->dev2;
     char* pin = h->pinned2;
     float* d_reg = reinterpret_cast<float*>(d);
@@ -313,117 +287,6 @@ extern "C" int tfrpn_proposals_host(tfrpn_handle h, const float* rpn_reg_host, c
     if (int rc = proposals_host_enqueue(h, rpn_reg_host, rpn_cls_host, anchors_dev, B, N, cfg, out_boxes_host,
                                         out_scores_host, valid_host, keep_idx_host_or_null, as_stream(s), job)) return rc;
     TFRPN_CHECK_CUDA(cudaStreamSynchronize(as_stream(s)));
-    job.finish();
-    return 0;
-}
-
-// One training/inference step from host buffers: both halves at once, pipelined over image chunks.
-//   caller's stream : H2D gt (tiny) -> for each chunk: targets kernels
-//   copy-out stream : D2H deltas/labels of chunk c as soon as its kernels are done (overlaps chunk c+1)
-//   copy-in stream  : H2D rpn_reg/rpn_cls of chunk c
-//   side stream     : proposals of chunk c as soon as its inputs have landed; one small D2H at the end
-// so the two large PCIe transfers (11 MB each way at C2) run concurrently in opposite directions and
-// only ~one chunk of compute is exposed.  Results are identical to the two separate calls: the counter
-// RNG is keyed by the global image index (image_offset), and images are independent.
-static int make_stream(cudaStream_t* s) {
-    if (!*s) TFRPN_CHECK_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
-    return 0;
-}
-
-extern "C" int tfrpn_rpn_step_host(tfrpn_handle h, const float* anchors_dev, const float* gt_boxes_host,
-                                   const int32_t* gt_labels_host, int B, int N, int G,
-                                   const tfrpn_target_cfg* tcfg, float* deltas_host, float* labels_host,
-                                   const float* rpn_reg_host, const float* rpn_cls_host,
-                                   const tfrpn_proposal_cfg* pcfg, float* out_boxes_host, float* out_scores_host,
-                                   int32_t* valid_host, int32_t* keep_idx_host_or_null, tfrpn_stream s) {
-    if (!h) return fail(TFRPN_ERR_BAD_ARG, "rpn_step_host: null handle");
-    if (!gt_boxes_host || !gt_labels_host || !deltas_host || !labels_host || !tcfg || !rpn_reg_host || !rpn_cls_host ||
-        !pcfg || !out_boxes_host || !out_scores_host || !valid_host)
-        return fail(TFRPN_ERR_BAD_ARG, "rpn_step_host: null pointer");
-    if (B <= 0 || N <= 0 || G <= 0 || pcfg->post_nms_topn <= 0) return fail(TFRPN_ERR_BAD_ARG, "rpn_step_host: bad shape");
-    cudaStream_t st = as_stream(s);
-    if (int rc = make_stream(&h->side)) return rc;
-    if (int rc = make_stream(&h->copy_in)) return rc;
-    if (int rc = make_stream(&h->copy_out)) return rc;
-    if (!h->ev_fork) {
-        TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-        TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
-        TFRPN_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
-    }
-    const int P = pcfg->post_nms_topn;
-    // staging: region 1 = target half, region 2 = proposal half
-    const size_t b_gt = align256((size_t)B * G * 16), b_gl = align256((size_t)B * G * 4);
-    const size_t b_d = align256((size_t)B * N * 16), b_l = align256((size_t)B * N * 4);
-    const size_t b_reg = align256((size_t)B * N * 16), b_cls = align256((size_t)B * N * 4);
-    const size_t b_ob = align256((size_t)B * P * 16), b_os = align256((size_t)B * P * 4);
-    const size_t b_v = align256((size_t)B * 4), b_k = align256((size_t)B * P * 4);
-    if (int rc = grow(&h->dev, &h->dev_bytes, b_gt + b_gl + b_d + b_l, st, false)) return rc;
-    if (int rc = grow(&h->pinned, &h->pinned_bytes, b_gt + b_gl + b_d + b_l, st, true)) return rc;
-    if (int rc = grow(&h->dev2, &h->dev2_bytes, b_reg + b_cls + b_ob + b_os + b_v + b_k, st, false)) return rc;
-    if (int rc = grow(&h->pinned2, &h->pinned2_bytes, b_reg + b_cls + b_ob + b_os + b_v + b_k, st, true)) return rc;
-    if (int rc = tfrpn_reserve(h, B, N, G, 0)) return rc;
-    float* d_gt = reinterpret_cast<float*>(h->dev);
-    int32_t* d_gl = reinterpret_cast<int32_t*>(h->dev + b_gt);
-    float* d_d = reinterpret_cast<float*>(h->dev + b_gt + b_gl);
-    float* d_l = reinterpret_cast<float*>(h->dev + b_gt + b_gl + b_d);
-    float* d_reg = reinterpret_cast<float*>(h->dev2);
-    float* d_cls = reinterpret_cast<float*>(h->dev2 + b_reg);
-    char* d_out = h->dev2 + b_reg + b_cls;
-    float* d_ob = reinterpret_cast<float*>(d_out);
-    float* d_os = reinterpret_cast<float*>(d_out + b_ob);
-    int32_t* d_v = reinterpret_cast<int32_t*>(d_out + b_ob + b_os);
-    int32_t* d_k = reinterpret_cast<int32_t*>(d_out + b_ob + b_os + b_v);
-    char* pin1 = h->pinned;
-    char* pin2 = h->pinned2;
-
-    const int chunks = B >= 32 ? 4 : (B >= 8 ? 2 : 1);
-    HostJob job;
-    // everything below is ordered after the caller's prior work on `st`
-    TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_fork, st));
-    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->copy_in, h->ev_fork, 0));
-    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_fork, 0));
-    if (int rc = h2d(d_gt, gt_boxes_host, (size_t)B * G * 16, pin1, st)) return rc;
-    if (int rc = h2d(d_gl, gt_labels_host, (size_t)B * G * 4, pin1 + b_gt, st)) return rc;
-    for (int c = 0; c < chunks; ++c) {
-        const int lo = (int)((long long)B * c / chunks), hi = (int)((long long)B * (c + 1) / chunks), nb = hi - lo;
-        if (nb == 0) continue;
-        // proposal half: inputs of this chunk, then its kernel
-        if (int rc = h2d(d_reg + (size_t)lo * N * 4, rpn_reg_host + (size_t)lo * N * 4, (size_t)nb * N * 16,
-                         pin2 + (size_t)lo * N * 16, h->copy_in)) return rc;
-        if (int rc = h2d(d_cls + (size_t)lo * N, rpn_cls_host + (size_t)lo * N, (size_t)nb * N * 4,
-                         pin2 + b_reg + (size_t)lo * N * 4, h->copy_in)) return rc;
-        TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_a, h->copy_in));
-        TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->side, h->ev_a, 0));
-        if (int rc = tfrpn_proposals(h, d_reg + (size_t)lo * N * 4, d_cls + (size_t)lo * N, anchors_dev, nb, N, pcfg,
-                                     d_ob + (size_t)lo * P * 4, d_os + (size_t)lo * P, d_v + lo, d_k + (size_t)lo * P,
-                                     h->side)) return rc;
-        // target half: kernels of this chunk, then its results go home while the next chunk computes
-        tfrpn_target_cfg cc = *tcfg;
-        cc.image_offset = tcfg->image_offset + lo;
-        if (int rc = tfrpn_rpn_targets(h, anchors_dev, d_gt + (size_t)lo * G * 4, d_gl + (size_t)lo * G, nb, N, G, &cc,
-                                       d_d + (size_t)lo * N * 4, d_l + (size_t)lo * N, nullptr, st)) return rc;
-        TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_b, st));
-        TFRPN_CHECK_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_b, 0));
-        if (int rc = d2h(deltas_host + (size_t)lo * N * 4, d_d + (size_t)lo * N * 4, (size_t)nb * N * 16,
-                         pin1 + b_gt + b_gl + (size_t)lo * N * 16, h->copy_out, job)) return rc;
-        if (int rc = d2h(labels_host + (size_t)lo * N, d_l + (size_t)lo * N, (size_t)nb * N * 4,
-                         pin1 + b_gt + b_gl + b_d + (size_t)lo * N * 4, h->copy_out, job)) return rc;
-    }
-    // the four small proposal results come back in ONE D2H copy through pinned staging
-    char* p_out = pin2 + b_reg + b_cls;
-    TFRPN_CHECK_CUDA(cudaMemcpyAsync(p_out, d_out, b_ob + b_os + b_v + b_k, cudaMemcpyDeviceToHost, h->side));
-    job.add(out_boxes_host, p_out, (size_t)B * P * 16);
-    job.add(out_scores_host, p_out + b_ob, (size_t)B * P * 4);
-    job.add(valid_host, p_out + b_ob + b_os, (size_t)B * 4);
-    if (keep_idx_host_or_null) job.add(keep_idx_host_or_null, p_out + b_ob + b_os + b_v, (size_t)B * P * 4);
-    // join everything back into the caller's stream
-    TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_join, h->side));
-    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
-    TFRPN_CHECK_CUDA(cudaEventRecord(h->ev_a, h->copy_out));
-    TFRPN_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_a, 0));
-    TFRPN_CHECK_CUDA(cudaStreamSynchronize(st));
     job.finish();
     return 0;
 }

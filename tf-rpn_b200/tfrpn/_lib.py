@@ -38,6 +38,11 @@ class ProposalCfg(C.Structure):
                 ("nms_iou_threshold", C.c_float), ("clip", C.c_int32)]
 
 
+class StepBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("gt_boxes", "gt_labels", "rpn_reg", "rpn_cls", "deltas", "labels",
+                                          "out_boxes", "out_scores", "valid", "keep_idx")]
+
+
 P = C.c_void_p
 I = C.c_int
 # name -> (restype, argtypes); must list every symbol include/tfrpn.h declares
@@ -66,6 +71,14 @@ PROTOTYPES = {
     "tfrpn_rpn_targets_host": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P]),
     "tfrpn_proposals_host": (I, [P, P, P, P, I, I, C.POINTER(ProposalCfg), P, P, P, P, P]),
     "tfrpn_rpn_step_host": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P, P, C.POINTER(ProposalCfg), P, P, P, P, P]),
+    "tfrpn_pipeline_create": (I, [P, I, C.POINTER(P)]),
+    "tfrpn_pipeline_submit": (I, [P, P, I, I, P, P, I, C.POINTER(TargetCfg), P, P, P, P, C.POINTER(ProposalCfg),
+                                  P, P, P, P, C.POINTER(C.c_int64)]),
+    "tfrpn_pipeline_acquire": (I, [P, I, I, I, I, C.POINTER(StepBuffers)]),
+    "tfrpn_pipeline_submit_acquired": (I, [P, P, C.POINTER(TargetCfg), C.POINTER(ProposalCfg), C.POINTER(C.c_int64)]),
+    "tfrpn_pipeline_wait": (I, [P, C.c_int64]),
+    "tfrpn_pipeline_drain": (I, [P]),
+    "tfrpn_pipeline_destroy": (I, [P]),
     "tfrpn_host_alloc": (I, [C.POINTER(P), C.c_size_t]),
     "tfrpn_host_free": (I, [P]),
 }

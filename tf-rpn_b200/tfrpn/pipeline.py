@@ -1,0 +1,134 @@
+"""Pipelined host steps: the generator call site of the reference (utils/train_utils.py:67-82, driven by
+Keras from trainer.py:48-49,64-69) and the predictor loop (predictor.py:48-60), over the C-ABI
+``tfrpn_pipeline_*`` entry points.
+
+A step moves ~11 MB over PCIe each way at C2 while its kernels take ~0.1 ms, so several steps are kept
+in flight: the H2D copy of step i+1 runs under the D2H copy of step i.  ``acquire()`` hands out NumPy
+views of one slot's page-locked buffers -- the data loader writes the padded batch (and the head outputs)
+straight into them and reads the results from them, so a step is exactly one copy per direction.
+"""
+import collections
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._tensor import default_device
+from .proposals import proposal_cfg
+from .utils import bbox_utils, train_utils
+
+StepViews = collections.namedtuple(
+    "StepViews", ["gt_boxes", "gt_labels", "rpn_reg", "rpn_cls", "deltas", "labels", "out_boxes", "out_scores",
+                  "valid", "keep_idx"])
+
+
+def _view(addr, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    return np.frombuffer((C.c_char * n).from_address(addr), dtype=dtype).reshape(shape)
+
+
+class HostPipeline:
+    """``depth`` host steps in flight on one GPU.
+
+        pipe = HostPipeline(hyper_params, depth=3)
+        v = pipe.acquire(B, G)              # NumPy views of the next slot's pinned buffers
+        v.gt_boxes[...] = ...; v.gt_labels[...] = ...; v.rpn_reg[...] = ...; v.rpn_cls[...] = ...
+        t = pipe.submit(offset=step)        # enqueue only; returns a ticket
+        ...                                 # acquire/fill/submit the next steps
+        pipe.wait(t)                        # v.deltas, v.labels, v.out_boxes ... now hold step t's results
+
+    The views of a slot stay valid until that slot is acquired again, ``depth`` steps later.
+    """
+
+    def __init__(self, hyper_params, depth=3, device=None, anchors=None, pre_nms_topn=None):
+        dev = default_device() if device is None else torch.device(device)
+        self.device = dev
+        self.hp = hyper_params
+        self.depth = int(depth)
+        with torch.cuda.device(dev):
+            self.anchors = bbox_utils.generate_anchors(hyper_params) if anchors is None else anchors
+            torch.cuda.synchronize()
+        self.N = int(self.anchors.shape[0])
+        self.pcfg = proposal_cfg(hyper_params, pre_nms_topn=pre_nms_topn)
+        self.P = int(self.pcfg.post_nms_topn)
+        self._lib = _lib.load()
+        self._h = _lib.handle(dev.index)
+        self._pipe = C.c_void_p()
+        _lib.check(self._lib.tfrpn_pipeline_create(self._h, self.depth, C.byref(self._pipe)))
+        self._views = {}
+
+    def acquire(self, batch, max_gt):
+        B, G, N, P = int(batch), int(max_gt), self.N, self.P
+        sb = _lib.StepBuffers()
+        _lib.check(self._lib.tfrpn_pipeline_acquire(self._pipe, B, N, G, P, C.byref(sb)))
+        key = (sb.gt_boxes, B, G)
+        v = self._views.get(key)
+        if v is None:
+            fm_h, fm_w = bbox_utils._pair(self.hp["feature_map_shape"])
+            A = int(self.hp["anchor_count"])
+            f32, i32 = np.float32, np.int32
+            v = StepViews(_view(sb.gt_boxes, (B, G, 4), f32), _view(sb.gt_labels, (B, G), i32),
+                          _view(sb.rpn_reg, (B, fm_h, fm_w, 4 * A), f32), _view(sb.rpn_cls, (B, fm_h, fm_w, A), f32),
+                          _view(sb.deltas, (B, N, 4), f32), _view(sb.labels, (B, fm_h, fm_w, A), f32),
+                          _view(sb.out_boxes, (B, P, 4), f32), _view(sb.out_scores, (B, P), f32),
+                          _view(sb.valid, (B,), i32), _view(sb.keep_idx, (B, P), i32))
+            if len(self._views) > 4 * self.depth:
+                self._views.clear()
+            self._views[key] = v
+        return v
+
+    def submit(self, targets=True, proposals=True, seed=None, offset=None, image_offset=0):
+        tcfg = train_utils._target_cfg(self.hp, seed, offset, image_offset) if targets else None
+        t = C.c_int64()
+        _lib.check(self._lib.tfrpn_pipeline_submit_acquired(
+            self._pipe, self.anchors.data_ptr(), C.byref(tcfg) if targets else None,
+            C.byref(self.pcfg) if proposals else None, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        _lib.check(self._lib.tfrpn_pipeline_wait(self._pipe, int(ticket)))
+
+    def drain(self):
+        _lib.check(self._lib.tfrpn_pipeline_drain(self._pipe))
+
+    def close(self):
+        if self._pipe:
+            self._lib.tfrpn_pipeline_destroy(self._pipe)
+            self._pipe = C.c_void_p()
+            self._views.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+def prefetching_rpn_generator(dataset, anchors, hyper_params, prefetch=2, seed=None):
+    """utils/train_utils.py:67-82 with the target assignment of the next ``prefetch`` batches already in
+    flight: yields ``(img, (bbox_deltas, bbox_labels))`` forever, like the reference.
+    ``dataset`` yields ``(img, gt_boxes (B,G,4), gt_labels (B,G))`` host arrays.  The yielded target arrays
+    are NumPy views of page-locked memory, valid until the next ``next()`` call (copy them to keep them)."""
+    pipe = HostPipeline(hyper_params, depth=int(prefetch) + 2, anchors=anchors)
+    pending = collections.deque()
+    step = 0
+    try:
+        while True:
+            for img, gt_boxes, gt_labels in dataset:
+                gt_boxes = np.asarray(gt_boxes, np.float32)
+                gt_labels = np.asarray(gt_labels, np.int32)
+                B, G = gt_labels.shape
+                v = pipe.acquire(B, G)
+                v.gt_boxes[...] = gt_boxes
+                v.gt_labels[...] = gt_labels
+                pending.append((pipe.submit(targets=True, proposals=False, seed=seed, offset=step), img, v))
+                step += 1
+                if len(pending) > prefetch:
+                    t, im, pv = pending.popleft()
+                    pipe.wait(t)
+                    yield im, (pv.deltas, pv.labels)
+            if step == 0:
+                return
+    finally:
+        pipe.close()

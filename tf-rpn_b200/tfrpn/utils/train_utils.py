@@ -73,8 +73,14 @@ def randomly_select_xyz_mask(mask, select_xyz, seed=0, offset=None, stream=0, im
     return from_device(out.to(torch.bool), o)
 
 
-def rpn_generator(dataset, anchors, hyper_params):
-    """utils/train_utils.py:67-82 (glue kept verbatim in behaviour: the call site of the path)."""
+def rpn_generator(dataset, anchors, hyper_params, prefetch=0):
+    """utils/train_utils.py:67-82 (glue kept verbatim in behaviour: the call site of the path).
+    ``prefetch`` > 0 (host batches only) keeps that many steps in flight through tfrpn.pipeline."""
+    if prefetch:
+        from ..pipeline import prefetching_rpn_generator
+        yield from prefetching_rpn_generator(dataset, anchors, hyper_params, prefetch=prefetch,
+                                             seed=hyper_params.get("seed", 0))
+        return
     while True:
         for image_data in dataset:
             img, gt_boxes, gt_labels = image_data
