@@ -109,7 +109,7 @@ TFRPN_API uint64_t tfrpn_launch_count(void);
 /* ---- tracing (the reference has none): when enabled, every kernel launched through
  *      this handle is bracketed by CUDA events on its stream.  Not usable during graph capture. */
 enum { TFRPN_K_IOU_ARGMAX = 0, TFRPN_K_LABEL_ENCODE = 1, TFRPN_K_SELECT_MASK = 2, TFRPN_K_PROPOSAL = 3,
-       TFRPN_K_COUNT = 4 };
+       TFRPN_K_LOSS = 4, TFRPN_K_COUNT = 5 };
 TFRPN_API int tfrpn_profile_enable(tfrpn_handle h, int on);
 /* synchronises, then returns the summed device time and launch count of one kernel id and clears them */
 TFRPN_API int tfrpn_profile_read(tfrpn_handle h, int kernel_id, double* total_ms, int* launches);
@@ -153,6 +153,26 @@ TFRPN_API int tfrpn_select_mask(tfrpn_handle h, const uint8_t* mask /* (B,N) 0/1
                       int n_select, int B, int N, uint64_t seed, uint64_t offset,
                       int rng_stream /* 0 = positives word, 1 = negatives word */,
                       int image_offset, uint8_t* out /* (B,N) */, tfrpn_stream s);
+
+/* ---- cls_loss + reg_loss: utils/train_utils.py:146-161 and :163-185 -------------------
+ * The consumers of tfrpn_rpn_targets' outputs.  cls: BinaryCrossentropy (Keras, probabilities,
+ * eps 1e-7) averaged over the entries with true label != -1 (NaN when there are none, as TF);
+ * reg: Huber(delta) summed over the 4 coordinates of the rows whose true delta is not all-zero,
+ * divided by max(1, #rows).  Either pair may be NULL to compute only the other loss.  Optional
+ * gradients with respect to the predictions (what TF autograd derives from the same ops). */
+typedef struct {
+    float reg_loss;  /* utils/train_utils.py:185 */
+    float cls_loss;  /* utils/train_utils.py:161 */
+    int32_t n_pos;   /* rows with a non-zero true delta (:180-184) */
+    int32_t n_cls;   /* entries with label != -1 (:156)            */
+} tfrpn_loss_out;
+TFRPN_API int tfrpn_rpn_losses(tfrpn_handle h, const float* true_deltas /* (B,N,4) or NULL */,
+                     const float* pred_deltas /* (B,N,4) == (B,F,F,4A) */,
+                     const float* true_labels /* (B,N) == (B,F,F,A) or NULL */,
+                     const float* pred_scores /* (B,N) */, int B, int N, float huber_delta /* 1.0f */,
+                     tfrpn_loss_out* out /* device, 16 bytes */,
+                     float* grad_deltas_or_null /* (B,N,4) */, float* grad_scores_or_null /* (B,N) */,
+                     tfrpn_stream s);
 
 /* ---- tf.nn.top_k + tf.gather(batch_dims=1): predictor.py:58-60 --------------------- */
 TFRPN_API int tfrpn_topk(tfrpn_handle h, const float* scores /* (B,N) */, int B, int N, int k,

@@ -401,3 +401,73 @@ def generate_proposals(rpn_reg, rpn_cls, anchors, hp, pre_nms_topn=None, post_nm
         return_indices=True)
     keep = np.where(ni >= 0, np.take_along_axis(top_idx, np.maximum(ni, 0).astype(np.int64), axis=1), -1)
     return nb, ns, nv, keep.astype(np.int32)
+
+
+# ---- losses (SURVEY 8f rank 1) -------------------------------------------------------------------
+def _bce_terms(t, p):
+    """[TF-internal] Keras backend.binary_crossentropy(from_logits=False) of TF 2.0.0, float32:
+    p = clip(p, eps, 1 - eps); -(t*log(p + eps) + (1 - t)*log(1 - p + eps)), eps = 1e-7."""
+    eps = F32(1e-7)
+    p = np.clip(p.astype(F32), eps, F32(1) - eps)
+    t = t.astype(F32)
+    bce = t * np.log(p + eps)
+    bce = bce + (F32(1) - t) * np.log(F32(1) - p + eps)
+    return -bce
+
+
+def cls_loss(y_true, y_pred):
+    """utils/train_utils.py:146-161.  Entries with y_true != -1 (:156) -> BinaryCrossentropy, mean
+    over them (:159-161).  The per-entry terms are float32 in TF's op order; the sum is carried
+    in float64 (TF sums in float32 in an unspecified order), so compare at ~1e-6 relative."""
+    t = np.asarray(y_true, F32).reshape(-1)
+    p = np.asarray(y_pred, F32).reshape(-1)
+    m = t != F32(-1.0)
+    terms = _bce_terms(t[m], p[m])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return F32(np.sum(terms, dtype=np.float64) / np.float64(terms.size))     # 0/0 -> NaN, as TF
+
+
+def _huber_terms(t, p, delta=1.0):
+    """[TF-internal] keras huber_loss of TF 2.0.0: elementwise (no mean over the last axis)."""
+    delta = F32(delta)
+    ae = np.abs(p.astype(F32) - t.astype(F32))
+    q = np.minimum(ae, delta)
+    lin = ae - q
+    return F32(0.5) * (q * q) + delta * lin
+
+
+def reg_loss(y_true, y_pred, delta=1.0):
+    """utils/train_utils.py:163-185.  y_pred reshaped to (B,-1,4) (:175); Huber per coordinate,
+    summed over the 4 coordinates (:178); rows with any non-zero true delta (:180-181);
+    sum / max(1, #rows) (:183-185)."""
+    t = np.asarray(y_true, F32)
+    p = np.asarray(y_pred, F32).reshape(t.shape[0], -1, 4)
+    h = _huber_terms(t, p, delta)
+    rows = ((h[..., 0] + h[..., 1]) + h[..., 2]) + h[..., 3]
+    pos = np.any(t != F32(0.0), axis=-1)
+    n = int(pos.sum())
+    return F32(np.sum(rows[pos], dtype=np.float64) / np.float64(max(1, n)))
+
+
+def loss_grads(true_deltas, pred_deltas, true_labels, pred_labels, delta=1.0):
+    """d reg_loss / d pred_deltas and d cls_loss / d pred_labels as TF's autograd derives them from
+    the ops above: Huber' = e for |e| <= delta else delta*sign(e) (minimum routes the gradient to
+    its first argument on ties), masked and / max(1, #pos); BCE' = ((1-t)/(1-p+eps) - t/(p+eps)) / M
+    inside the clip range [eps, 1-eps] (clip_by_value passes the gradient on its closed range)."""
+    t = np.asarray(true_deltas, F32)
+    p = np.asarray(pred_deltas, F32).reshape(t.shape)
+    e = p - t
+    pos = np.any(t != F32(0.0), axis=-1, keepdims=True)
+    g = np.where(np.abs(e) <= F32(delta), e, np.where(e > 0, F32(delta), -F32(delta))).astype(F32)
+    inv = F32(1.0) / F32(max(1, int(pos.sum())))
+    gd = np.where(pos, g * inv, F32(0.0)).astype(F32).reshape(np.asarray(pred_deltas).shape)
+    tl = np.asarray(true_labels, F32)
+    pl = np.asarray(pred_labels, F32)
+    eps = F32(1e-7)
+    valid = tl != F32(-1.0)
+    inside = (pl >= eps) & (pl <= F32(1) - eps)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        gb = (F32(1) - tl) / ((F32(1) - pl) + eps) - tl / (pl + eps)
+        invm = F32(1.0) / F32(int(valid.sum()))
+        gl = np.where(valid, np.where(inside, gb, F32(0.0)) * invm, F32(0.0)).astype(F32)
+    return gd, gl

@@ -629,3 +629,77 @@ def test_prefetching_rpn_generator_matches_reference_generator(T):
         od, ol = O.calculate_rpn_actual_outputs(anchors_np, gtb, gtl, hp, seed=5, offset=step)
         assert bits_equal(labels, ol) and close(deltas, od)
     gen.close()
+
+
+# ---------------------------------------------------------------- losses
+# Per-entry terms are float32 in the reference's op order (logf within 2 ulp of Eigen's log); the
+# sums are carried in float64 on both sides, so the scalar losses agree to ~1e-6 relative.
+LOSS_RTOL = 2e-6
+
+
+def loss_close(got, want, rtol=LOSS_RTOL):
+    got, want = float(got), float(want)
+    return (np.isnan(got) and np.isnan(want)) or abs(got - want) <= rtol * max(abs(want), 1e-30)
+
+
+def test_losses_match_golden(T, golden):
+    """cls_loss / reg_loss with the reference's signatures on the vectors its own source produced."""
+    reg = T.train.reg_loss(T.cu(golden["loss_reg_true"]), T.cu(golden["loss_reg_pred"]))
+    cls = T.train.cls_loss((T.cu(golden["loss_cls_true"]), T.cu(golden["loss_cls_pred"])))    # ((y_true, y_pred),) form
+    assert reg.shape == () and cls.shape == ()
+    assert loss_close(T.np(reg), golden["loss_reg"]) and loss_close(T.np(cls), golden["loss_cls"])
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3"])
+def test_losses_on_real_targets(T, cfg):
+    """Losses of synthetic head outputs against the targets the CUDA path itself assigned."""
+    from tfrpn import synthetic
+    bb, B, G, over = synthetic.CONFIGS[cfg]
+    B = min(B, 16)
+    hp = dict(O.get_hyper_params(bb), **over)
+    rng = np.random.default_rng(77)
+    anchors = O.generate_anchors(hp)
+    gtb, gtl = synthetic.gt_batch(rng, B, G)
+    fm = hp["feature_map_shape"]
+    reg, cls = synthetic.head_outputs(rng, B, fm, fm, 9)
+    deltas, labels = T.train.calculate_rpn_actual_outputs(T.cu(anchors), T.cu(gtb), T.cu(gtl), hp, seed=3, offset=0)
+    r = T.train.rpn_losses(deltas, T.cu(reg), labels, T.cu(cls), with_grads=True)
+    d_np, l_np = T.np(deltas), T.np(labels)
+    assert loss_close(T.np(r["reg_loss"]), O.reg_loss(d_np, reg))
+    assert loss_close(T.np(r["cls_loss"]), O.cls_loss(l_np, cls))
+    assert int(r["n_pos"]) == int(np.any(d_np != 0, axis=-1).sum()) and int(r["n_cls"]) == int((l_np != -1).sum())
+    gd, gl = O.loss_grads(d_np, reg, l_np, cls)
+    assert r["grad_deltas"].shape == reg.shape and r["grad_labels"].shape == cls.shape
+    assert close(T.np(r["grad_deltas"]), gd) and close(T.np(r["grad_labels"]), gl)
+    # the single-loss entry points give the same numbers
+    assert bits_equal(T.np(T.train.reg_loss(deltas, T.cu(reg))), T.np(r["reg_loss"]))
+    assert bits_equal(T.np(T.train.cls_loss(labels, T.cu(cls))), T.np(r["cls_loss"]))
+
+
+def test_losses_edge_cases(T):
+    rng = np.random.default_rng(5)
+    # no positives, no valid labels: reg = 0 / max(1, 0), cls = mean of nothing = NaN (as TF)
+    t = np.zeros((2, 33, 4), F32)
+    p = rng.normal(size=(2, 33, 4)).astype(F32)
+    lab = np.full((2, 33), -1, F32)
+    sc = rng.uniform(size=(2, 33)).astype(F32)
+    r = T.train.rpn_losses(T.cu(t), T.cu(p), T.cu(lab), T.cu(sc), with_grads=True)
+    assert float(r["reg_loss"]) == 0.0 and np.isnan(float(r["cls_loss"]))
+    assert not T.np(r["grad_deltas"]).any() and not T.np(r["grad_labels"]).any()
+    # scores outside (eps, 1 - eps) are clipped and get no gradient; Huber kink at |e| == delta
+    lab = np.array([[1, 0, 1, 0, -1]], F32)
+    sc = np.array([[0.0, 1.0, 1.0, 0.0, 0.5]], F32)
+    t = np.zeros((1, 5, 4), F32)
+    t[0, 0] = [1, 0, 0, 0]
+    p = np.zeros((1, 5, 4), F32)
+    p[0, 0] = [2, -1, 1, 5]          # e = [1, -1, 1, 5]
+    r = T.train.rpn_losses(T.cu(t), T.cu(p), T.cu(lab), T.cu(sc), with_grads=True)
+    assert loss_close(T.np(r["cls_loss"]), O.cls_loss(lab, sc)) and loss_close(T.np(r["reg_loss"]), O.reg_loss(t, p))
+    gd, gl = O.loss_grads(t, p, lab, sc)
+    assert bits_equal(T.np(r["grad_deltas"]), gd) and bits_equal(T.np(r["grad_labels"]), gl)
+    assert np.array_equal(T.np(r["grad_deltas"])[0, 0], np.array([1, -1, 1, 1], F32))
+    # NumPy in -> NumPy out, like every other drop-in
+    out = T.train.reg_loss(t, p)
+    assert isinstance(out, np.ndarray) and loss_close(out, O.reg_loss(t, p))
+    with pytest.raises(ValueError):
+        T.train.rpn_losses(T.cu(t), T.cu(p[:, :4]))

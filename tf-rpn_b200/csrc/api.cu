@@ -112,6 +112,7 @@ extern "C" const char* tfrpn_kernel_name(int id) {
         case TFRPN_K_LABEL_ENCODE: return "rpn_label_encode_kernel";
         case TFRPN_K_SELECT_MASK: return "select_mask_kernel";
         case TFRPN_K_PROPOSAL: return "proposal_kernel";
+        case TFRPN_K_LOSS: return "rpn_loss_partial_kernel";
         default: return "?";
     }
 }

@@ -38,6 +38,10 @@ class ProposalCfg(C.Structure):
                 ("nms_iou_threshold", C.c_float), ("clip", C.c_int32)]
 
 
+class LossOut(C.Structure):
+    _fields_ = [("reg_loss", C.c_float), ("cls_loss", C.c_float), ("n_pos", C.c_int32), ("n_cls", C.c_int32)]
+
+
 class StepBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("gt_boxes", "gt_labels", "rpn_reg", "rpn_cls", "deltas", "labels",
                                           "out_boxes", "out_scores", "valid", "keep_idx")]
@@ -65,6 +69,7 @@ PROTOTYPES = {
     "tfrpn_scale_boxes": (I, [P, C.c_int64, C.c_float, C.c_float, I, P, P]),
     "tfrpn_rpn_targets": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, C.POINTER(TargetDebug), P]),
     "tfrpn_select_mask": (I, [P, P, P, I, I, I, C.c_uint64, C.c_uint64, I, I, P, P]),
+    "tfrpn_rpn_losses": (I, [P, P, P, P, P, I, I, C.c_float, P, P, P, P]),
     "tfrpn_topk": (I, [P, P, I, I, I, P, P, P, I, P, P]),
     "tfrpn_nms": (I, [P, P, P, I, I, C.POINTER(NmsCfg), P, P, P, P, P, P]),
     "tfrpn_proposals": (I, [P, P, P, P, I, I, C.POINTER(ProposalCfg), P, P, P, P, P]),

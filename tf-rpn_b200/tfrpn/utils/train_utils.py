@@ -148,3 +148,72 @@ def calculate_rpn_actual_outputs(anchors, gt_boxes, gt_labels, hyper_params, see
     if return_debug:
         return out + ({k: from_device(v, o) for k, v in dbg.items()},)
     return out
+
+
+def _loss_args(args):
+    """The reference accepts (y_true, y_pred) or ((y_true, y_pred),) (utils/train_utils.py:156,174)."""
+    y_true, y_pred = args if len(args) == 2 else args[0]
+    return y_true, y_pred
+
+
+def rpn_losses(true_deltas=None, pred_deltas=None, true_labels=None, pred_labels=None, huber_delta=1.0,
+               with_grads=False):
+    """Both RPN losses (utils/train_utils.py:146-185) in one pass over the target tensors.
+
+    true_deltas (B,N,4) / pred_deltas (B,...) reshaped to (B,N,4) as reg_loss does (:175);
+    true_labels / pred_labels any matching shape, e.g. (B,F,F,A).  Either pair may be None.
+    Returns a dict with 0-d ``reg_loss`` / ``cls_loss`` tensors, ``n_pos`` / ``n_cls`` counts and,
+    with ``with_grads``, ``grad_deltas`` / ``grad_labels`` (d loss / d prediction, prediction-shaped).
+    """
+    o = Origin()
+    td = pd = tl = pl = None
+    B = N = None
+    pd_shape = pl_shape = None
+    if true_deltas is not None:
+        td = to_device(true_deltas, F32, o, "true_deltas")
+        pd = to_device(pred_deltas, F32, o, "pred_deltas")
+        pd_shape = tuple(pd.shape)
+        if td.dim() != 3 or td.shape[-1] != 4 or pd.numel() != td.numel() or pd.shape[0] != td.shape[0]:
+            raise ValueError("true_deltas must be (B,N,4) and pred_deltas reshapeable to it")
+        B, N = td.shape[:2]
+    if true_labels is not None:
+        tl = to_device(true_labels, F32, o, "true_labels")
+        pl = to_device(pred_labels, F32, o, "pred_labels")
+        pl_shape = tuple(pl.shape)
+        if tl.shape != pl.shape:
+            raise ValueError("true_labels and pred_labels must have the same shape")
+        if B is None:
+            B, N = 1, tl.numel()      # cls_loss is a flat mean: the batch split does not matter
+        elif tl.numel() != B * N:
+            raise ValueError("labels (%d entries) do not match deltas (%d rows)" % (tl.numel(), B * N))
+    if B is None:
+        raise ValueError("rpn_losses needs at least one (true, predicted) pair")
+    dev = (td if td is not None else tl).device
+    out = torch.empty((4,), dtype=F32, device=dev)
+    gd = torch.empty_like(pd) if (with_grads and pd is not None) else None
+    gl = torch.empty_like(pl) if (with_grads and pl is not None) else None
+    _lib.check(_lib.load().tfrpn_rpn_losses(_lib.handle(dev.index), ptr(td), ptr(pd), ptr(tl), ptr(pl), B, N,
+                                            float(huber_delta), ptr(out), ptr(gd), ptr(gl), stream_ptr(dev)))
+    counts = out.view(torch.int32)
+    res = {"n_pos": from_device(counts[2], o), "n_cls": from_device(counts[3], o)}
+    if td is not None:
+        res["reg_loss"] = from_device(out[0], o)
+    if tl is not None:
+        res["cls_loss"] = from_device(out[1], o)
+    if gd is not None:
+        res["grad_deltas"] = from_device(gd.reshape(pd_shape), o)
+    if gl is not None:
+        res["grad_labels"] = from_device(gl.reshape(pl_shape), o)
+    return res
+
+
+def cls_loss(*args):
+    """utils/train_utils.py:146-161: BinaryCrossentropy over the entries whose true label is not -1."""
+    y_true, y_pred = _loss_args(args)
+    return rpn_losses(true_labels=y_true, pred_labels=y_pred)["cls_loss"]
+
+
+def reg_loss(*args):
+    """utils/train_utils.py:163-185: Huber over the rows with a non-zero true delta / max(1, #rows)."""
+    y_true, y_pred = _loss_args(args)
+    return rpn_losses(true_deltas=y_true, pred_deltas=y_pred)["reg_loss"]
