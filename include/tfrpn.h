@@ -180,6 +180,23 @@ TFRPN_API int tfrpn_topk(tfrpn_handle h, const float* scores /* (B,N) */, int B,
                const float* boxes_or_null /* (N,4) or (B,N,4) */, int boxes_batched,
                float* gathered_or_null /* (B,k,4) */, tfrpn_stream s);
 
+/* ---- the predictor loop body, predictor.py:52-60, in one launch: reshape, deltas *= variances,
+ *      get_bboxes_from_deltas, tf.nn.top_k(rpn_labels, k), tf.gather(batch_dims=1).  Only the k
+ *      selected rows are decoded.  clip = 0 reproduces the reference (it never clips). --------- */
+TFRPN_API int tfrpn_predict_topk(tfrpn_handle h, const float* rpn_reg /* (B,N,4) == (B,F,F,4A) */,
+                       const float* rpn_cls /* (B,N) == (B,F,F,A) */, const float* anchors /* (N,4) */,
+                       int B, int N, int k, const float* variances_host /* [4] */, int clip,
+                       float* out_boxes /* (B,k,4) */, float* out_scores /* (B,k) */,
+                       int32_t* out_indices /* (B,k) */, tfrpn_stream s);
+
+/* ---- GT-side preprocessing: utils/data_utils.py:54-68 (flip_horizontally's box transform) and
+ *      :145-157 (padded_batch with boxes 0 / labels -1).  Ragged input: image b owns rows
+ *      offsets[b] .. offsets[b+1] of the flat arrays; rows beyond G are dropped. ---------------- */
+TFRPN_API int tfrpn_pad_gt(const float* flat_boxes /* (M,4) */, const int32_t* flat_labels /* (M,) */,
+                 const int32_t* offsets /* (B+1,) */, const uint8_t* flip_or_null /* (B,) 0/1 */,
+                 int B, int G, int label_add /* data_utils.py:20 uses +1 */,
+                 float* out_boxes /* (B,G,4) */, int32_t* out_labels /* (B,G) */, tfrpn_stream s);
+
 /* ---- non_max_suppression: utils/bbox_utils.py:48-70 (1 class, q = 1) ---------------
  * rows = cfg->pad_per_class ? min(max_total_size, per_class) : max_total_size          */
 TFRPN_API int tfrpn_nms(tfrpn_handle h, const float* boxes /* (B,K,4) */, const float* scores /* (B,K) */,

@@ -471,3 +471,41 @@ def loss_grads(true_deltas, pred_deltas, true_labels, pred_labels, delta=1.0):
         invm = F32(1.0) / F32(int(valid.sum()))
         gl = np.where(valid, np.where(inside, gb, F32(0.0)) * invm, F32(0.0)).astype(F32)
     return gd, gl
+
+
+# ---- the callers either side of the path ----------------------------------
+def predictor_top_boxes(rpn_bbox_deltas, rpn_labels, anchors, hp, k=10):
+    """predictor.py:52-60: reshape (:52-53), deltas *= variances (:55), get_bboxes_from_deltas (:56),
+    tf.nn.top_k(rpn_labels, k) (:58, [TF-internal] ties -> lower index first), gather (:60).
+    Returns (selected_rpn_bboxes (B,k,4), top_values (B,k), top_indices (B,k) int32)."""
+    reg = np.asarray(rpn_bbox_deltas, F32)
+    B = reg.shape[0]
+    reg = reg.reshape(B, -1, 4) * np.asarray(hp["variances"], F32)
+    cls = np.asarray(rpn_labels, F32).reshape(B, -1)
+    boxes = get_bboxes_from_deltas(np.asarray(anchors, F32), reg)
+    vals, idx = top_k(cls, k)
+    return np.take_along_axis(boxes, idx[..., None].astype(np.int64), axis=1), vals, idx
+
+
+def flip_horizontally_boxes(gt_boxes):
+    """utils/data_utils.py:66-69: [y1, 1 - x2, y2, 1 - x1] in float32."""
+    b = np.asarray(gt_boxes, F32)
+    return np.stack([b[..., 0], F32(1.0) - b[..., 3], b[..., 2], F32(1.0) - b[..., 1]], axis=-1)
+
+
+def pad_gt_batch(gt_boxes_list, gt_labels_list, max_boxes=None, flip=None, label_add=0):
+    """tf.data padded_batch with utils/data_utils.py:152-157's padding values (boxes 0, labels -1),
+    optional per-image flip (:54-68) and the ``label + 1`` of preprocessing (:20)."""
+    B = len(gt_boxes_list)
+    G = int(max_boxes) if max_boxes is not None else max([len(b) for b in gt_boxes_list] + [1])
+    boxes = np.zeros((B, G, 4), F32)
+    labels = np.full((B, G), -1, np.int32)
+    for b in range(B):
+        n = min(len(gt_boxes_list[b]), G)
+        if n:
+            bx = np.asarray(gt_boxes_list[b], F32)[:n]
+            if flip is not None and flip[b]:
+                bx = flip_horizontally_boxes(bx)
+            boxes[b, :n] = bx
+            labels[b, :n] = np.asarray(gt_labels_list[b], np.int32)[:n] + np.int32(label_add)
+    return boxes, labels

@@ -392,6 +392,11 @@ def _iou_scalar(bx, i, j):
 
 class image:  # noqa: N801
     @staticmethod
+    def flip_left_right(img):
+        """Reverse the width axis (axis -2 of (..., H, W, C)); used by utils/data_utils.py:65."""
+        return Tensor(np.flip(_t(img).a, axis=-2).copy())
+
+    @staticmethod
     def combined_non_max_suppression(boxes, scores, max_output_size_per_class, max_total_size,
                                      iou_threshold=0.5, score_threshold=float("-inf"),
                                      pad_per_class=False, clip_boxes=True, name=None):

@@ -703,3 +703,64 @@ def test_losses_edge_cases(T):
     assert isinstance(out, np.ndarray) and loss_close(out, O.reg_loss(t, p))
     with pytest.raises(ValueError):
         T.train.rpn_losses(T.cu(t), T.cu(p[:, :4]))
+
+
+# ---------------------------------------------------------------- callers either side
+@pytest.fixture(scope="module")
+def nxt():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return dict(np.load(os.path.join(root, "tests", "golden", "next_vectors.npz")))
+
+
+def test_predictor_body_matches_golden(T, nxt):
+    """tfrpn.predict_top_boxes == predictor.py:52-60 exec'd from the reference file (k = 10, no clip)."""
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors = T.bbox.generate_anchors(hp)
+    boxes, vals, idx = T.tfrpn.predict_top_boxes(T.cu(nxt["pred_reg"]), T.cu(nxt["pred_cls"]), anchors, hp, k=10)
+    assert np.array_equal(T.np(idx), nxt["pred_top_indices"])
+    assert close(T.np(boxes), nxt["pred_selected_bboxes"])
+    assert bits_equal(T.np(vals), np.take_along_axis(nxt["pred_cls"].reshape(3, -1), nxt["pred_top_indices"].astype(np.int64), axis=1))
+
+
+@pytest.mark.parametrize("B,k", [(2, 1), (5, 300), (3, 2000), (1, 8649)])
+def test_predictor_body_vs_oracle(T, B, k):
+    from tfrpn import synthetic
+    hp = dict(O.get_hyper_params("vgg16"))
+    a_np = O.generate_anchors(hp)
+    reg, cls = synthetic.head_outputs(np.random.default_rng(B * 31 + k), B, 31, 31, 9)
+    boxes, vals, idx = T.tfrpn.predict_top_boxes(T.cu(reg), T.cu(cls), T.cu(a_np), hp, k=k)
+    ob, ov, oi = O.predictor_top_boxes(reg, cls, a_np, hp, k=k)
+    assert np.array_equal(T.np(idx), oi) and bits_equal(T.np(vals), ov) and close(T.np(boxes), ob)
+    # same boxes as the unfused sequence decode -> top_k_boxes
+    var = T.cu(np.asarray(hp["variances"], F32))
+    full = T.bbox.get_bboxes_from_deltas(T.cu(a_np), T.cu(reg).reshape(B, -1, 4) * var)
+    _, idx2, gat = T.bbox.top_k_boxes(T.cu(cls).reshape(B, -1), k, full)
+    assert np.array_equal(T.np(idx2), oi) and bits_equal(T.np(gat), T.np(boxes))
+    cb, _, _ = T.tfrpn.predict_top_boxes(T.cu(reg), T.cu(cls), T.cu(a_np), hp, k=k, clip=True)
+    assert bits_equal(T.np(cb), np.clip(T.np(boxes), 0, 1))
+
+
+def test_gt_padding_and_flip(T, nxt):
+    from tfrpn.utils import data_utils
+    assert bits_equal(T.np(data_utils.flip_horizontally_boxes(T.cu(nxt["flip_in"]))), nxt["flip_out"])
+    rng = np.random.default_rng(9)
+    counts = [3, 0, 7, 1, 50]
+    bl = [rand_boxes(rng, n) for n in counts]
+    ll = [rng.integers(0, 20, size=n) for n in counts]
+    flip = [True, True, False, True, False]
+    for G, add in [(None, 1), (50, 0), (4, 1)]:
+        gb, gl = data_utils.pad_gt_batch(bl, ll, max_boxes=G, flip=flip, label_add=add)
+        ob, ol = O.pad_gt_batch(bl, ll, max_boxes=G, flip=flip, label_add=add)
+        assert bits_equal(T.np(gb), ob) and np.array_equal(T.np(gl), ol) and gl.dtype == T.torch.int32
+    # the padded batch feeds target assignment exactly like a host-padded one
+    hp = dict(O.get_hyper_params("vgg16"))
+    a_np = O.generate_anchors(hp)
+    gb, gl = data_utils.pad_gt_batch(bl, ll, flip=flip, label_add=1)
+    d, l = T.train.calculate_rpn_actual_outputs(T.cu(a_np), gb, gl, hp, seed=4, offset=2)
+    ob, ol = O.pad_gt_batch(bl, ll, flip=flip, label_add=1)
+    od, olab = O.calculate_rpn_actual_outputs(a_np, ob, ol, hp, seed=4, offset=2)
+    assert bits_equal(T.np(l), olab) and close(T.np(d), od)
+    # an all-empty batch still pads to G >= 1
+    gb, gl = data_utils.pad_gt_batch([np.zeros((0, 4), F32)] * 2, [np.zeros((0,), np.int32)] * 2)
+    assert gb.shape == (2, 1, 4) and not T.np(gb).any() and list(T.np(gl).ravel()) == [-1, -1]

@@ -199,6 +199,30 @@ __global__ void __launch_bounds__(EW_THREADS) scale_boxes_kernel(const float4* _
     }
 }
 
+// GT-side preprocessing (utils/data_utils.py:54-68 flip, :145-157 padded batch): ragged boxes /
+// labels (offsets[b] .. offsets[b+1]) -> (B,G,4) zero padded and (B,G) padded with -1.
+__global__ void __launch_bounds__(EW_THREADS) pad_gt_kernel(const float4* __restrict__ flat_boxes,
+                                                            const int* __restrict__ flat_labels,
+                                                            const int* __restrict__ offsets,
+                                                            const unsigned char* __restrict__ flip, int B, int G,
+                                                            int label_add, float4* __restrict__ out_boxes,
+                                                            int* __restrict__ out_labels) {
+    const int i = blockIdx.x * EW_THREADS + threadIdx.x;
+    if (i >= B * G) return;
+    const int b = i / G, g = i - b * G;
+    const int lo = __ldg(offsets + b), n = __ldg(offsets + b + 1) - lo;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);      // get_padding_values: boxes 0, labels -1
+    int lab = -1;
+    if (g < n) {
+        bx = ldg_f4(flat_boxes + lo + g);
+        lab = __ldg(flat_labels + lo + g) + label_add;
+        if (flip && flip[b])                            // [y1, 1 - x2, y2, 1 - x1], data_utils.py:66-69
+            bx = make_float4(bx.x, __fsub_rn(1.0f, bx.w), bx.z, __fsub_rn(1.0f, bx.y));
+    }
+    out_boxes[i] = bx;
+    out_labels[i] = lab;
+}
+
 static int ew_grid(long long total, int per_thread) {
     long long blocks = (total + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
     if (blocks < 1) blocks = 1;
@@ -322,5 +346,22 @@ extern "C" int tfrpn_scale_boxes(const float* boxes, int64_t n_boxes, float heig
     scale_boxes_kernel<<<ew_grid(n_boxes, 1), EW_THREADS, 0, as_stream(s)>>>(
         reinterpret_cast<const float4*>(boxes), n_boxes, height, width, denormalize, reinterpret_cast<float4*>(out));
     TFRPN_AFTER_LAUNCH("scale_boxes_kernel");
+    return 0;
+}
+
+extern "C" int tfrpn_pad_gt(const float* flat_boxes, const int32_t* flat_labels, const int32_t* offsets,
+                            const uint8_t* flip_or_null, int B, int G, int label_add, float* out_boxes,
+                            int32_t* out_labels, tfrpn_stream s) {
+    if (!offsets || !out_boxes || !out_labels) return fail(TFRPN_ERR_BAD_ARG, "pad_gt: null pointer");
+    if (B < 0 || G < 0) return fail(TFRPN_ERR_BAD_ARG, "pad_gt: negative shape");
+    if ((long long)B * G == 0) return 0;
+    if (!flat_boxes || !flat_labels) return fail(TFRPN_ERR_BAD_ARG, "pad_gt: null pointer");
+    if ((long long)B * G > (1LL << 30)) return fail(TFRPN_ERR_UNSUPPORTED, "pad_gt: B*G too large");
+    if (!aligned16(flat_boxes) || !aligned16(out_boxes)) return fail(TFRPN_ERR_MISALIGNED, "pad_gt: boxes must be 16-byte aligned");
+    const int blocks = (B * G + EW_THREADS - 1) / EW_THREADS;
+    pad_gt_kernel<<<blocks, EW_THREADS, 0, as_stream(s)>>>(reinterpret_cast<const float4*>(flat_boxes), flat_labels, offsets,
+                                                           flip_or_null, B, G, label_add,
+                                                           reinterpret_cast<float4*>(out_boxes), out_labels);
+    TFRPN_AFTER_LAUNCH("pad_gt_kernel");
     return 0;
 }

@@ -257,7 +257,14 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 const long long o = (long long)b * p.k + lo + tid;
                 p.values[o] = scores[my_i];
                 p.indices[o] = (int)my_i;
-                if (p.gathered) p.gathered[o] = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
+                if (p.gathered) {
+                    if (p.reg) {   // predictor.py:55-56 for the selected rows only: decode(anchor, delta * variances)
+                        float4 bx = decode_ref(ldg_f4(p.anchors + my_i), mul4(ldg_f4(p.reg + (long long)b * N + my_i), p.var));
+                        p.gathered[o] = p.clip_decoded ? clip01(bx) : bx;
+                    } else {
+                        p.gathered[o] = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
+                    }
+                }
             }
             __syncthreads();   // sortbuf is rewritten by the next batch
             continue;
@@ -452,6 +459,26 @@ extern "C" int tfrpn_topk(tfrpn_handle h, const float* scores, int B, int N, int
     p.mode = MODE_TOPK; p.N = N; p.k = k; p.scores = scores; p.use_sthr = 0;
     p.boxes = reinterpret_cast<const float4*>(boxes_or_null); p.box_stride = boxes_batched ? N : 0;
     p.values = values; p.indices = indices; p.gathered = reinterpret_cast<float4*>(gathered_or_null);
+    p.max_out = 0; p.rows = 0;
+    return launch(h, p, B, as_stream(s));
+}
+
+extern "C" int tfrpn_predict_topk(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B,
+                                  int N, int k, const float* variances_host, int clip, float* out_boxes,
+                                  float* out_scores, int32_t* out_indices, tfrpn_stream s) {
+    if (!rpn_reg || !rpn_cls || !anchors || !variances_host || !out_boxes || !out_scores || !out_indices)
+        return fail(TFRPN_ERR_BAD_ARG, "predict_topk: null pointer");
+    if (B < 0 || N < 0 || k < 0) return fail(TFRPN_ERR_BAD_ARG, "predict_topk: negative shape");
+    if (k > N) return fail(TFRPN_ERR_BAD_ARG, "predict_topk: k=%d > N=%d (tf.nn.top_k raises InvalidArgumentError too)", k, N);
+    if (!aligned16(rpn_reg) || !aligned16(anchors) || !aligned16(out_boxes))
+        return fail(TFRPN_ERR_MISALIGNED, "predict_topk: rpn_reg / anchors / out_boxes must be 16-byte aligned");
+    if (B == 0 || k == 0) return 0;
+    PropParams p = {};
+    p.mode = MODE_TOPK; p.N = N; p.k = k; p.scores = rpn_cls; p.use_sthr = 0;
+    p.reg = reinterpret_cast<const float4*>(rpn_reg); p.anchors = reinterpret_cast<const float4*>(anchors);
+    p.var = make_float4(variances_host[0], variances_host[1], variances_host[2], variances_host[3]);
+    p.clip_decoded = clip;
+    p.values = out_scores; p.indices = out_indices; p.gathered = reinterpret_cast<float4*>(out_boxes);
     p.max_out = 0; p.rows = 0;
     return launch(h, p, B, as_stream(s));
 }

@@ -6,8 +6,8 @@ and run on hand-written CUDA kernels in libtfrpn_cuda.so through the C ABI of in
 There is no CPU implementation in this package.
 """
 from . import _lib  # noqa: F401
-from .utils import bbox_utils, train_utils  # noqa: F401
-from .proposals import generate_proposals  # noqa: F401
+from .utils import bbox_utils, data_utils, train_utils  # noqa: F401
+from .proposals import generate_proposals, predict_top_boxes  # noqa: F401
 from .pipeline import HostPipeline, prefetching_rpn_generator  # noqa: F401
 
 __version__ = "0.1.0"

@@ -71,6 +71,8 @@ PROTOTYPES = {
     "tfrpn_select_mask": (I, [P, P, P, I, I, I, C.c_uint64, C.c_uint64, I, I, P, P]),
     "tfrpn_rpn_losses": (I, [P, P, P, P, P, I, I, C.c_float, P, P, P, P]),
     "tfrpn_topk": (I, [P, P, I, I, I, P, P, P, I, P, P]),
+    "tfrpn_predict_topk": (I, [P, P, P, P, I, I, I, P, I, P, P, P, P]),
+    "tfrpn_pad_gt": (I, [P, P, P, P, I, I, I, P, P, P]),
     "tfrpn_nms": (I, [P, P, P, I, I, C.POINTER(NmsCfg), P, P, P, P, P, P]),
     "tfrpn_proposals": (I, [P, P, P, P, I, I, C.POINTER(ProposalCfg), P, P, P, P, P]),
     "tfrpn_rpn_targets_host": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P]),

@@ -54,3 +54,36 @@ def generate_proposals(rpn_bbox_deltas, rpn_labels, anchors, hyper_params, pre_n
                                            C.byref(cfg), ptr(boxes), ptr(scores), ptr(valid), ptr(keep),
                                            stream_ptr(dev)))
     return tuple(from_device(t, o) for t in (boxes, scores, valid, keep))
+
+
+def predict_top_boxes(rpn_bbox_deltas, rpn_labels, anchors, hyper_params, k=10, clip=False):
+    """The body of the reference's predictor loop, predictor.py:52-60, in one launch:
+
+        rpn_bbox_deltas = reshape(.., (B,-1,4)); rpn_labels = reshape(.., (B,-1))      (:52-53)
+        rpn_bbox_deltas *= variances; rpn_bboxes = get_bboxes_from_deltas(anchors, ..)  (:55-56)
+        _, top_indices = tf.nn.top_k(rpn_labels, 10)                                    (:58)
+        selected_rpn_bboxes = tf.gather(rpn_bboxes, top_indices, batch_dims=1)          (:60)
+
+    Only the k selected rows are decoded.  Returns (selected_rpn_bboxes (B,k,4), top_values (B,k),
+    top_indices (B,k) int32).  ``clip`` defaults to False because the reference never clips here.
+    """
+    o = Origin()
+    reg = to_device(rpn_bbox_deltas, F32, o, "rpn_bbox_deltas")
+    cls = to_device(rpn_labels, F32, o, "rpn_labels")
+    anc = to_device(anchors, F32, o, "anchors")
+    B = reg.shape[0]
+    reg = reg.reshape(B, -1, 4)
+    cls = cls.reshape(B, -1)
+    N = cls.shape[1]
+    if reg.shape[1] != N or anc.shape != (N, 4):
+        raise ValueError("shapes disagree: deltas %s, labels %s, anchors %s"
+                         % (tuple(reg.shape), tuple(cls.shape), tuple(anc.shape)))
+    k = int(k)
+    dev = reg.device
+    boxes = torch.empty((B, k, 4), dtype=F32, device=dev)
+    vals = torch.empty((B, k), dtype=F32, device=dev)
+    idx = torch.empty((B, k), dtype=torch.int32, device=dev)
+    var = (C.c_float * 4)(*[float(v) for v in hyper_params["variances"]])
+    _lib.check(_lib.load().tfrpn_predict_topk(_lib.handle(dev.index), ptr(reg), ptr(cls), ptr(anc), B, N, k, var,
+                                              int(bool(clip)), ptr(boxes), ptr(vals), ptr(idx), stream_ptr(dev)))
+    return tuple(from_device(t, o) for t in (boxes, vals, idx))
