@@ -282,7 +282,7 @@ def run_ours(args):
         targets(sets[i % SETS], i, cur_s)
         proposals(sets[i % SETS], cur_s)
     kern = {}
-    for kid in range(4):
+    for kid in range(4):   # the kernels of the step (ids of include/tfrpn.h)
         tot, n = C.c_double(), C.c_int()
         _lib.check(lib.tfrpn_profile_read(h, kid, C.byref(tot), C.byref(n)))
         if n.value:
@@ -295,11 +295,21 @@ def run_ours(args):
     dominant = max(kern, key=kern.get)
     dom_us = kern[dominant]
     achieved = alg[dominant] / (dom_us * 1e-6) / 1e9
+    # measured DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    # capture, summarised by tools/summarize_profiles.py into profiles/traffic.json); null if not captured
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch", {})
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "us_per_launch": dom_us,
-                "algorithmic_bytes": alg[dominant], "peak_source": peak_src}
+                "frac": achieved / hbm_peak, "traffic": traffic.get(dominant), "us_per_launch": dom_us,
+                "algorithmic_bytes": alg[dominant], "peak_source": peak_src,
+                "note": "one CTA per image; bound by per-image latency (select / sort / sequential greedy NMS), not by HBM"
+                        if dominant == "proposal_kernel" else ""}
     kernels = [{"kernel": k, "us_per_launch": v, "algorithmic_bytes": alg[k],
-                "achieved_gbs": alg[k] / (v * 1e-6) / 1e9, "frac_hbm": alg[k] / (v * 1e-6) / 1e9 / hbm_peak}
+                "achieved_gbs": alg[k] / (v * 1e-6) / 1e9, "frac_hbm": alg[k] / (v * 1e-6) / 1e9 / hbm_peak,
+                "traffic": traffic.get(k)}
                for k, v in kern.items()]
     # the IoU/argmax kernel is FP32-ALU bound (B*N*G pairs x ~22 lane-instr), say so
     if "rpn_iou_argmax_kernel" in kern:
@@ -344,6 +354,16 @@ def run_ours(args):
                                                                sets[r % SETS]["deltas"].data_ptr(), cur)), 10 * SETS)
     by = 32 * B * N + 16 * N
     kernels.append({"kernel": "decode_kernel", "us_per_launch": us, "algorithmic_bytes": by,
+                    "achieved_gbs": by / (us * 1e-6) / 1e9, "frac_hbm": by / (us * 1e-6) / 1e9 / hbm_peak})
+
+    # the losses that consume the targets: reads labels + true deltas, predictions only
+    # where a term exists; 3 launches (partials, final, nothing else without gradients)
+    lout = torch.empty((4,), device=dev)
+    us = timed_loop(lambda r, cur: _lib.check(lib.tfrpn_rpn_losses(h, sets[r % SETS]["deltas"].data_ptr(), sets[r % SETS]["reg"].data_ptr(),
+                                                                   sets[r % SETS]["labels"].data_ptr(), sets[r % SETS]["cls"].data_ptr(),
+                                                                   B, N, 1.0, lout.data_ptr(), None, None, cur)), 10 * SETS)
+    by = 20 * B * N
+    kernels.append({"kernel": "rpn_loss_partial_kernel+final", "us_per_launch": us, "algorithmic_bytes": by,
                     "achieved_gbs": by / (us * 1e-6) / 1e9, "frac_hbm": by / (us * 1e-6) / 1e9 / hbm_peak})
 
     # ---- e2e: host buffers through the C-ABI host entry points, copies inside the timed region ----
@@ -413,6 +433,7 @@ def run_ours(args):
     Ke = min(K, 400)
     pipelined(2 * DEPTH)
     t_e2e = wall(pipelined, Ke)
+    h2d_pipe, d2h_pipe = pipe.last_copy_bytes()
     for i in range(3):
         sync_step(i)
     Ks = min(K, 100)
@@ -420,13 +441,17 @@ def run_ours(args):
     pipe.close()
     h2d = B * G * 16 + B * G * 4 + B * N * 16 + B * N * 4
     d2h = B * N * 16 + B * N * 4 + B * P * 16 + B * P * 4 + B * 4 + B * P * 4
-    e2e = {"value": world * B * Ke / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+    e2e = {"value": world * B * Ke / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_pipe, "d2h_bytes_per_step": d2h_pipe,
            "steps": Ke, "ms_per_step": 1e3 * t_e2e / Ke,
-           "pcie_gbs_each_way": [h2d * Ke / t_e2e / 1e9, d2h * Ke / t_e2e / 1e9],
+           "pcie_gbs_each_way": [h2d_pipe * Ke / t_e2e / 1e9, d2h_pipe * Ke / t_e2e / 1e9],
+           "dense_result_bytes_per_step": d2h,
            "api": "tfrpn.HostPipeline acquire/submit/wait (tfrpn_pipeline_* C ABI), %d host steps in flight, inputs and "
-                  "results in the slots' page-locked host blocks: one H2D + one D2H copy per step" % DEPTH,
+                  "results in the slots' page-locked host blocks: one H2D + one D2H copy per step; bbox_deltas "
+                  "crosses PCIe in compact form (its <=128 non-zero rows per image) and wait() scatters it into the "
+                  "dense (B,N,4) host array inside the timed region" % DEPTH,
            "one_step_at_a_time": {"value": world * B * Ks / t_sync, "ms_per_step": 1e3 * t_sync / Ks,
-                                  "api": "tfrpn_rpn_step_host (synchronous: returns with the results in host memory)"}}
+                                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                  "api": "tfrpn_rpn_step_host (synchronous: returns with the dense results in host memory)"}}
 
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

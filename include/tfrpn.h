@@ -147,6 +147,20 @@ TFRPN_API int tfrpn_rpn_targets(tfrpn_handle h, const float* anchors /* (N,4) */
                       float* deltas /* (B,N,4) */, float* labels /* (B,N) == (B,F,F,A) */,
                       const tfrpn_target_debug* dbg_or_null, tfrpn_stream s);
 
+/* Compact form of bbox_deltas, for callers that move the results over PCIe: it is exactly 0 outside
+ * the <= total_pos sampled positives of each image (utils/train_utils.py:137), so only those rows travel,
+ * as (anchor index, row) pairs; the rows of an image are in no particular order and unused index slots
+ * are -1.  bbox_labels is returned as usual.  tfrpn_expand_targets_host rebuilds the dense tensor on the
+ * host: with prev_pos_idx (the pos_idx of the step whose rows `deltas` still holds, prev_total_pos
+ * columns) only those rows are cleared first, otherwise the whole array is zeroed. */
+TFRPN_API int tfrpn_rpn_targets_compact(tfrpn_handle h, const float* anchors, const float* gt_boxes,
+                              const int32_t* gt_labels, int B, int N, int G, const tfrpn_target_cfg* cfg,
+                              float* labels /* (B,N) */, int32_t* pos_idx /* (B,total_pos) */,
+                              float* pos_deltas /* (B,total_pos,4) */, tfrpn_stream s);
+TFRPN_API int tfrpn_expand_targets_host(const int32_t* pos_idx, const float* pos_deltas, int B, int N, int total_pos,
+                              const int32_t* prev_pos_idx_or_null, int prev_total_pos,
+                              float* deltas /* (B,N,4) host */);
+
 /* ---- randomly_select_xyz_mask: utils/train_utils.py:50-65 (counter RNG) ------------ */
 TFRPN_API int tfrpn_select_mask(tfrpn_handle h, const uint8_t* mask /* (B,N) 0/1 */,
                       const int32_t* select /* (n_select,) device; n_select = 1 or B */,
@@ -253,7 +267,8 @@ TFRPN_API int tfrpn_pipeline_submit(tfrpn_pipeline p, const float* anchors_dev /
                           int32_t* keep_idx_host_or_null, int64_t* ticket_out);
 /* Zero-copy variant: borrow the next slot's page-locked step buffers, fill the inputs in place (the
  * data loader writes its padded batch / the head outputs straight into them), submit, and after
- * wait() read the results in place.  Inputs are one contiguous block and results another, so a step
+ * wait() read the results in place (do not write to the result arrays: the library keeps them
+ * consistent incrementally from step to step).  Inputs are one contiguous block and results another, so a step
  * is exactly ONE H2D and ONE D2H copy -- the pattern that reaches the link's duplex rate.  The
  * pointers stay valid until the slot is acquired again (depth steps later).  tcfg / pcfg NULL skips
  * that half. */
@@ -274,6 +289,9 @@ TFRPN_API int tfrpn_pipeline_submit_acquired(tfrpn_pipeline p, const float* anch
                                    const tfrpn_target_cfg* tcfg_or_null, const tfrpn_proposal_cfg* pcfg_or_null,
                                    int64_t* ticket_out);
 TFRPN_API int tfrpn_pipeline_wait(tfrpn_pipeline p, int64_t ticket);
+/* bytes the last submitted acquired step copies in each direction (bbox_deltas travels in compact form,
+ * see tfrpn_rpn_targets_compact, and is expanded into the slot's dense host array by wait()) */
+TFRPN_API int tfrpn_pipeline_last_copy_bytes(tfrpn_pipeline p, int64_t* h2d_bytes, int64_t* d2h_bytes);
 TFRPN_API int tfrpn_pipeline_drain(tfrpn_pipeline p); /* wait for every step in flight */
 TFRPN_API int tfrpn_pipeline_destroy(tfrpn_pipeline p);
 /* page-locked host memory for the caller's batches (so H2D/D2H run at full PCIe rate) */

@@ -23,12 +23,16 @@
 
 namespace tfrpn {
 size_t targets_workspace_bytes(int B, int N, int G);  // targets.cu
+int launch_targets(tfrpn_handle h, const float* anchors, const float* gt_boxes, const int32_t* gt_labels, int B, int N,
+                   int G, const tfrpn_target_cfg* cfg, float* deltas, float* labels, int32_t* pos_idx,
+                   float* pos_deltas, const tfrpn_target_debug* dbg, tfrpn_stream s);
 }
 
 namespace {
 
 constexpr int MAX_CHUNKS = 8;
 constexpr int MAX_DEPTH = 8;
+constexpr int COMPACT_MAX_POS = 256;   // compact result form is used when total_pos_bboxes <= this
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -45,6 +49,15 @@ struct Slot {
     cudaEvent_t ev_gt = nullptr, ev_prop = nullptr, ev_done = nullptr;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_tgt[MAX_CHUNKS] = {};
     long long ticket = -1;          // ticket in flight in this slot (-1 = free)
+    // compact results (acquired mode): bbox_deltas comes back as its <= total_pos non-zero rows per image and is
+    // expanded into the slot's dense host array when the step is retired (the labels travel as they are)
+    bool compact = false;           // the step in flight returns compact targets
+    int cB = 0, cN = 0, cTP = 0;    // its shape
+    size_t off_d = 0, off_ci = 0, off_cd = 0;
+    bool dense_clean = false;       // pin + off_d holds zeros except the rows listed in prev_idx
+    int pB = 0, pN = 0, pTP = 0;
+    size_t p_off_d = 0;
+    std::vector<int32_t> prev_idx;
     struct Copy { void* dst; const void* src; size_t bytes; } copies[8 + 2 * MAX_CHUNKS];
     int n_copies = 0;
     void defer(void* d, const void* s, size_t b) { copies[n_copies].dst = d; copies[n_copies].src = s; copies[n_copies].bytes = b; ++n_copies; }
@@ -61,6 +74,7 @@ struct tfrpn_pipe {
     long long next_ticket = 0;
     int acq_B = 0, acq_N = 0, acq_G = 0, acq_P = 0;   // shape of the slot handed out by the last acquire()
     bool acq_live = false;
+    long long last_h2d = 0, last_d2h = 0;             // bytes copied by the last submitted step
 };
 
 namespace tfrpn {
@@ -116,6 +130,17 @@ static int slot_finish(tfrpn_pipe* p, Slot& s) {
     TFRPN_CHECK_CUDA(cudaEventSynchronize(s.ev_done));
     for (int i = 0; i < s.n_copies; ++i) memcpy(s.copies[i].dst, s.copies[i].src, s.copies[i].bytes);
     s.n_copies = 0;
+    if (s.compact) {   // expand into the dense (B,N,4) / (B,N) host arrays of this slot
+        const bool reuse = s.dense_clean && s.pB == s.cB && s.pN == s.cN && s.p_off_d == s.off_d;
+        const int32_t* idx = reinterpret_cast<const int32_t*>(s.pin + s.off_ci);
+        if (int rc = tfrpn_expand_targets_host(idx, reinterpret_cast<const float*>(s.pin + s.off_cd), s.cB, s.cN, s.cTP,
+                                               reuse ? s.prev_idx.data() : nullptr, reuse ? s.pTP : 0,
+                                               reinterpret_cast<float*>(s.pin + s.off_d))) return rc;
+        s.prev_idx.assign(idx, idx + (size_t)s.cB * s.cTP);
+        s.pB = s.cB; s.pN = s.cN; s.pTP = s.cTP; s.p_off_d = s.off_d;
+        s.dense_clean = true;
+        s.compact = false;
+    }
     s.ticket = -1;
     return 0;
 }
@@ -136,7 +161,8 @@ struct StepArgs {
 // rate (tools/src/pcie_pattern.cu: 309 us vs 231 us per C2 step).
 struct Layout {
     size_t gt, gl, reg, cls, in_end;            // inputs
-    size_t d, l, ob, os, v, k, total;           // results
+    size_t d, l, ob, os, v, k, dense_end;       // results
+    size_t ci, cd, total;                       // compact bbox_deltas (row indices, rows)
 };
 static Layout make_layout(int B, int N, int G, int P) {
     Layout L;
@@ -152,6 +178,9 @@ static Layout make_layout(int B, int N, int G, int P) {
     L.os = o;  o += align256((size_t)B * P * 4);
     L.v = o;   o += align256((size_t)B * 4);
     L.k = o;   o += align256((size_t)B * P * 4);
+    L.dense_end = o;
+    L.ci = o;  o += align256((size_t)B * COMPACT_MAX_POS * 4);
+    L.cd = o;  o += align256((size_t)B * COMPACT_MAX_POS * 16);
     L.total = o;
     return L;
 }
@@ -162,6 +191,7 @@ static int slot_reserve(tfrpn_pipe* p, Slot& s, size_t total) {
     for (int i = 0; i < p->depth; ++i) if (int rc = slot_finish(p, p->slots[i])) return rc;
     if (int rc = grow_buffer(&s.dev, &s.dev_bytes, total, p->s_out, false)) return rc;
     if (int rc = grow_buffer(&s.pin, &s.pin_bytes, total, p->s_out, true)) return rc;
+    s.dense_clean = false;   // new host block: nothing is known about its contents
     return 0;
 }
 
@@ -212,6 +242,12 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         for (cudaStream_t st : {p->s_in, p->s_tgt, p->s_prop, p->s_out}) TFRPN_CHECK_CUDA(cudaStreamWaitEvent(st, p->ev_after, 0));
     }
     s.n_copies = 0;
+    // Acquired slots return bbox_deltas in compact form (2.8 MB of results instead of 11.5 MB per C2 step: the
+    // deltas are exactly zero outside the <= total_pos sampled positives, utils/train_utils.py:137);
+    // slot_finish expands them into the slot's dense host array.
+    static const bool force_dense = getenv("TFRPN_PIPE_DENSE") != nullptr;
+    const bool compact = acquired && do_t && !force_dense && a.tcfg->total_pos <= COMPACT_MAX_POS;
+    if (do_t && !compact) s.dense_clean = false;   // the dense arrays are about to be overwritten wholesale
     // A synchronous step (depth 1) is chunked over images so that copies overlap its own kernels; with
     // several steps in flight the overlap comes from the neighbouring steps and fewer, larger copies win.
     int chunks = (p->depth == 1 && !acquired) ? (B >= 32 ? 4 : (B >= 8 ? 2 : 1)) : 1;
@@ -251,7 +287,12 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         if (do_t) {
             tfrpn_target_cfg cc = *a.tcfg;
             cc.image_offset = a.tcfg->image_offset + lo;
-            if (int rc = tfrpn_rpn_targets(h, a.anchors_dev, reinterpret_cast<const float*>(d + L.gt) + (size_t)lo * G * 4,
+            if (compact) {   // (acquired => one chunk)
+                if (int rc = launch_targets(h, a.anchors_dev, reinterpret_cast<const float*>(d + L.gt),
+                                            reinterpret_cast<const int32_t*>(d + L.gl), nb, N, G, &cc, nullptr,
+                                            reinterpret_cast<float*>(d + L.l), reinterpret_cast<int32_t*>(d + L.ci),
+                                            reinterpret_cast<float*>(d + L.cd), nullptr, p->s_tgt)) return rc;
+            } else if (int rc = tfrpn_rpn_targets(h, a.anchors_dev, reinterpret_cast<const float*>(d + L.gt) + (size_t)lo * G * 4,
                                            reinterpret_cast<const int32_t*>(d + L.gl) + (size_t)lo * G, nb, N, G, &cc,
                                            reinterpret_cast<float*>(d + L.d) + (size_t)lo * N * 4,
                                            reinterpret_cast<float*>(d + L.l) + (size_t)lo * N, nullptr, p->s_tgt)) return rc;
@@ -276,8 +317,16 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         }
     }
     if (acquired) {   // one copy for all results of the halves that ran
-        const size_t lo = do_t ? L.d : L.ob, hi = do_p ? L.total : L.ob;
+        size_t lo = do_t ? L.d : L.ob, hi = do_p ? L.dense_end : L.ob;
+        if (compact) {   // labels, [proposal results,] row indices, rows: one contiguous range
+            lo = L.l;
+            hi = L.cd + (size_t)B * a.tcfg->total_pos * 16;
+            s.compact = true; s.cB = B; s.cN = N; s.cTP = a.tcfg->total_pos;
+            s.off_d = L.d; s.off_ci = L.ci; s.off_cd = L.cd;
+        }
         TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin + lo, d + lo, hi - lo, cudaMemcpyDeviceToHost, p->s_out));
+        p->last_d2h = (long long)(hi - lo);
+        p->last_h2d = (long long)((do_p ? L.in_end : L.reg) - (do_t ? L.gt : L.reg));
     }
     TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_done, p->s_out));
     s.ticket = p->next_ticket++;
@@ -368,6 +417,13 @@ extern "C" int tfrpn_pipeline_submit_acquired(tfrpn_pipeline p, const float* anc
     if (int rc = pipe_submit(p, a, true, false, nullptr, &t)) return rc;
     p->acq_live = false;
     if (ticket_out) *ticket_out = t;
+    return 0;
+}
+
+extern "C" int tfrpn_pipeline_last_copy_bytes(tfrpn_pipeline p, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!p || !h2d_bytes || !d2h_bytes) return fail(TFRPN_ERR_BAD_ARG, "pipeline_last_copy_bytes: null pointer");
+    *h2d_bytes = p->last_h2d;
+    *d2h_bytes = p->last_d2h;
     return 0;
 }
 

@@ -68,6 +68,8 @@ PROTOTYPES = {
     "tfrpn_decode": (I, [P, I, P, P, I, I, I, P, P]),
     "tfrpn_scale_boxes": (I, [P, C.c_int64, C.c_float, C.c_float, I, P, P]),
     "tfrpn_rpn_targets": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, C.POINTER(TargetDebug), P]),
+    "tfrpn_rpn_targets_compact": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P, P]),
+    "tfrpn_expand_targets_host": (I, [P, P, I, I, I, P, I, P]),
     "tfrpn_select_mask": (I, [P, P, P, I, I, I, C.c_uint64, C.c_uint64, I, I, P, P]),
     "tfrpn_rpn_losses": (I, [P, P, P, P, P, I, I, C.c_float, P, P, P, P]),
     "tfrpn_topk": (I, [P, P, I, I, I, P, P, P, I, P, P]),
@@ -84,6 +86,7 @@ PROTOTYPES = {
     "tfrpn_pipeline_acquire": (I, [P, I, I, I, I, C.POINTER(StepBuffers)]),
     "tfrpn_pipeline_submit_acquired": (I, [P, P, C.POINTER(TargetCfg), C.POINTER(ProposalCfg), C.POINTER(C.c_int64)]),
     "tfrpn_pipeline_wait": (I, [P, C.c_int64]),
+    "tfrpn_pipeline_last_copy_bytes": (I, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tfrpn_pipeline_drain": (I, [P]),
     "tfrpn_pipeline_destroy": (I, [P]),
     "tfrpn_host_alloc": (I, [C.POINTER(P), C.c_size_t]),

@@ -40,7 +40,7 @@ def main():
         sets.append([torch.from_numpy(a).to(dev) for a in (gtb, gtl, reg, cls)])
     for i in range(args.steps):
         gtb, gtl, reg, cls = sets[i % 3]
-        train_utils.calculate_rpn_actual_outputs(anchors, gtb, gtl, hp, seed=1, offset=i)
+        deltas, labels = train_utils.calculate_rpn_actual_outputs(anchors, gtb, gtl, hp, seed=1, offset=i)
         tfrpn.generate_proposals(reg, cls, anchors, hp)
         if args.extras:
             bbox_utils.generate_iou_map(anchors, gtb)
@@ -48,6 +48,8 @@ def main():
             boxes = bbox_utils.get_bboxes_from_deltas(anchors, reg.reshape(B, -1, 4) * var)
             bbox_utils.get_deltas_from_bboxes(anchors, boxes)
             bbox_utils.top_k_boxes(cls.reshape(B, -1), 6000, boxes)
+            train_utils.rpn_losses(deltas, reg, labels, cls, with_grads=True)
+            tfrpn.predict_top_boxes(reg, cls, anchors, hp, k=10)
     torch.cuda.synchronize()
     print("done", tfrpn._lib.launch_count(), "launches")
 

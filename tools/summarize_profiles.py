@@ -50,4 +50,15 @@ with open(os.path.join(ROOT, "profiles", tag + "_kernels.csv"), "w") as f:
     w.writerow(["%s [%s]" % (n, U[i]) if U[i] else n for n, i in idx])
     for r in data:
         w.writerow([r[i][:90] for _, i in idx])
-print("wrote profiles/%s_launches.csv and profiles/%s_kernels.csv" % (tag, tag))
+# DRAM bytes per launch (read + write), averaged per kernel -> profiles/traffic.json (bench.py's roofline.traffic)
+import json
+unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+ri, wi, ki = H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), H.index("Kernel Name")
+acc = collections.OrderedDict()
+for r in data:
+    name = r[ki].split("(")[0].split("<")[0].replace("void ", "").strip()
+    acc.setdefault(name, []).append(float(r[ri]) * unit[U[ri]] + float(r[wi]) * unit[U[wi]])
+with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+    json.dump({"source": "profiles/%s_kernels.csv (ncu --set full --clock-control none, per launch)" % tag,
+               "dram_bytes_per_launch": {k: round(sum(v) / len(v)) for k, v in acc.items()}}, f, indent=1)
+print("wrote profiles/%s_launches.csv, profiles/%s_kernels.csv and profiles/traffic.json" % (tag, tag))
