@@ -82,3 +82,29 @@ def test_hyper_params_quirks_match_reference():
     assert hp["anchor_count"] == 9 and hp["test_nms_topn"] == 300
     train_utils.get_hyper_params("vgg16", total_pos_bboxes=128)
     assert train_utils.get_step_size(10, 4) == 3
+
+
+def test_expand_targets_host_matches_numpy_scatter():
+    """tfrpn_expand_targets_host is host-only code: the dense bbox_deltas from its compact form, both from
+    scratch and incrementally on top of the previous step's rows."""
+    import numpy as np
+    from tfrpn import _lib
+    lib = _lib.load()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rng = np.random.default_rng(3)
+    B, N = 5, 700
+    deltas = rng.normal(size=(B, N, 4)).astype(np.float32)        # garbage: the first call must zero it
+    prev, prev_tp = None, 0
+    for step, TP in enumerate([16, 16, 40, 8]):
+        idx = np.full((B, TP), -1, np.int32)
+        rows = rng.normal(size=(B, TP, 4)).astype(np.float32)
+        want = np.zeros((B, N, 4), np.float32)
+        for b in range(B):
+            k = int(rng.integers(0, TP + 1))
+            idx[b, :k] = rng.choice(N, k, replace=False)
+            want[b, idx[b, :k]] = rows[b, :k]
+        rc = lib.tfrpn_expand_targets_host(vp(idx), vp(rows), B, N, TP, vp(prev) if prev is not None else None, prev_tp,
+                                           vp(deltas))
+        assert rc == 0 and np.array_equal(deltas, want), step
+        prev, prev_tp = idx, TP
+    assert lib.tfrpn_expand_targets_host(None, None, 1, 1, 1, None, 0, None) == -1

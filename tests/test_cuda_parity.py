@@ -764,3 +764,37 @@ def test_gt_padding_and_flip(T, nxt):
     # an all-empty batch still pads to G >= 1
     gb, gl = data_utils.pad_gt_batch([np.zeros((0, 4), F32)] * 2, [np.zeros((0,), np.int32)] * 2)
     assert gb.shape == (2, 1, 4) and not T.np(gb).any() and list(T.np(gl).ravel()) == [-1, -1]
+
+
+def test_targets_compact_form_equals_dense(T):
+    """tfrpn_rpn_targets_compact: same labels, and scattering its (index, row) pairs gives bbox_deltas bit for bit."""
+    import ctypes as C
+    from tfrpn import _lib, synthetic
+    hp = dict(O.get_hyper_params("vgg16"))
+    a_np = O.generate_anchors(hp)
+    B, G, N, TP = 6, 20, a_np.shape[0], hp["total_pos_bboxes"]
+    gtb, gtl = synthetic.gt_batch(np.random.default_rng(21), B, G)
+    gtb[2], gtl[2] = 0, -1                                     # an image without ground truth: no rows at all
+    anchors, dgtb, dgtl = T.cu(a_np), T.cu(gtb), T.cu(gtl)
+    d, l = T.train.calculate_rpn_actual_outputs(anchors, dgtb, dgtl, hp, seed=9, offset=4)
+    cfg = T.train._target_cfg(hp, 9, 4, 0)
+    labels = T.torch.empty((B, N), device=T.dev)
+    idx = T.torch.empty((B, TP), dtype=T.torch.int32, device=T.dev)
+    rows = T.torch.empty((B, TP, 4), device=T.dev)
+    lib = _lib.load()
+    _lib.check(lib.tfrpn_rpn_targets_compact(_lib.handle(0), anchors.data_ptr(), dgtb.data_ptr(), dgtl.data_ptr(), B, N, G,
+                                             C.byref(cfg), labels.data_ptr(), idx.data_ptr(), rows.data_ptr(),
+                                             T.torch.cuda.current_stream().cuda_stream))
+    assert bits_equal(T.np(labels).reshape(T.np(l).shape), T.np(l))
+    idx_np, rows_np, d_np = T.np(idx), T.np(rows), T.np(d)
+    dense = np.zeros((B, N, 4), F32)
+    for b in range(B):
+        k = int((idx_np[b] >= 0).sum())
+        assert np.all(idx_np[b, :k] >= 0) and np.all(idx_np[b, k:] == -1) and len(set(idx_np[b, :k])) == k
+        assert k == int((T.np(l)[b] == 1).sum())
+        dense[b, idx_np[b, :k]] = rows_np[b, :k]
+    assert bits_equal(dense, d_np) and (idx_np[2] == -1).all()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    host = np.empty((B, N, 4), F32)
+    assert lib.tfrpn_expand_targets_host(vp(idx_np), vp(rows_np), B, N, TP, None, 0, vp(host)) == 0
+    assert bits_equal(host, d_np)
