@@ -190,28 +190,42 @@ def run_ours(args):
     set_bytes = sum(t.numel() * t.element_size() for t in sets[0].values())
     _lib.check(lib.tfrpn_reserve(h, B, N, G, PRE_NMS))
     pcfg = proposal_cfg(hp, pre_nms_topn=PRE_NMS)
-    side = torch.cuda.Stream(dev)
+    # LANES independent steps are in flight at a time (consecutive batches do not depend on each other): each
+    # lane has its own library handle (= its own workspace), a stream for the target half and a high-priority
+    # stream for the proposal half, whose 64 one-per-image CTAs need whole SMs and would otherwise queue behind
+    # the thousands of small IoU CTAs.
+    LANES = max(1, min(4, int(os.environ.get("TFRPN_BENCH_LANES", "4"))))
+    assert SETS % LANES == 0
+    handles, mains, sides = [h], [], []
+    for _ in range(1, LANES):
+        hh = C.c_void_p()
+        _lib.check(lib.tfrpn_create(C.byref(hh), local))
+        _lib.check(lib.tfrpn_reserve(hh, B, N, G, PRE_NMS))
+        handles.append(hh)
+    for _ in range(LANES):
+        mains.append(torch.cuda.Stream(dev))
+        sides.append(torch.cuda.Stream(dev, priority=-1))
 
     def tcfg(step):
         return train_utils._target_cfg(hp, 2026, step, rank * B)
 
-    def targets(s, step, stream):
-        _lib.check(lib.tfrpn_rpn_targets(h, anchors.data_ptr(), s["gtb"].data_ptr(), s["gtl"].data_ptr(), B, N, G,
+    def targets(s, step, stream, hh=h):
+        _lib.check(lib.tfrpn_rpn_targets(hh, anchors.data_ptr(), s["gtb"].data_ptr(), s["gtl"].data_ptr(), B, N, G,
                                          C.byref(tcfg(step)), s["deltas"].data_ptr(), s["labels"].data_ptr(), None,
                                          stream.cuda_stream))
 
-    def proposals(s, stream):
-        _lib.check(lib.tfrpn_proposals(h, s["reg"].data_ptr(), s["cls"].data_ptr(), anchors.data_ptr(), B, N,
+    def proposals(s, stream, hh=h):
+        _lib.check(lib.tfrpn_proposals(hh, s["reg"].data_ptr(), s["cls"].data_ptr(), anchors.data_ptr(), B, N,
                                        C.byref(pcfg), s["pb"].data_ptr(), s["ps"].data_ptr(), s["pv"].data_ptr(),
                                        s["pk"].data_ptr(), stream.cuda_stream))
 
     def step_eager(i):
-        """targets on the current stream, proposals concurrently on a side stream (independent halves)."""
-        cur = torch.cuda.current_stream(dev)
-        s = sets[i % SETS]
+        """One step on lane i % LANES: targets on the lane's stream, proposals concurrently on its side stream."""
+        lane = i % LANES
+        cur, side, s = mains[lane], sides[lane], sets[i % SETS]
         side.wait_stream(cur)
-        targets(s, i, cur)
-        proposals(s, side)
+        targets(s, i, cur, handles[lane])
+        proposals(s, side, handles[lane])
         cur.wait_stream(side)
 
     # eager warm-up (also sets kernel attributes before any capture)
@@ -219,21 +233,26 @@ def run_ours(args):
     step_eager(0)
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - n0
+    for i in range(1, LANES):
+        step_eager(i)
+    torch.cuda.synchronize()
 
     graphs = None
     if not args.no_graph:
         graphs = []
         for i in range(SETS):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=mains[i % LANES]):
                 step_eager(i)
             graphs.append(g)
 
     def run_step(i):
         if graphs is not None:
-            graphs[i % SETS].replay()
+            with torch.cuda.stream(mains[i % LANES]):
+                graphs[i % SETS].replay()
         else:
             step_eager(i)
+        return mains[i % LANES]
 
     W, K = max(args.warmup, 3), max(args.steps, 1)
     for i in range(W):
@@ -247,12 +266,17 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur0 = torch.cuda.current_stream(dev)
     barrier()
     sampler.start()
-    e0.record()
+    e0.record(cur0)
+    for m in mains:
+        m.wait_stream(cur0)
     for i in range(K):
         run_step(W + i)
-    e1.record()
+    for m in mains:
+        cur0.wait_stream(m)
+    e1.record(cur0)
     barrier()
     clocks = sampler.result()
     ms = e0.elapsed_time(e1)
@@ -262,13 +286,14 @@ def run_ours(args):
         ms = float(t.item())
     value = world * B * K / (ms * 1e-3)
 
-    # ---- p50 single-step latency (device time per step, synchronised between steps) -------------
+    # ---- p50 single-step latency (device time of ONE step, the GPU idle before and after) ----------
     lat = []
     for i in range(min(K, 200)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        st = mains[i % LANES]
+        a.record(st)
         run_step(i)
-        b.record()
+        b.record(st)
         torch.cuda.synchronize()
         lat.append(a.elapsed_time(b))
     p50 = float(np.median(lat))
@@ -458,7 +483,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "images sharded, no collective",
                        "l2": "rotating %d input/output sets (%.0f MB) > 126 MB L2" % (SETS, SETS * set_bytes / 1e6),
-                       "launch": "eager" if graphs is None else "one CUDA graph per set; targets || proposals on two streams"},
+                       "launch": ("eager" if graphs is None else "one CUDA graph per step") +
+                                 "; targets || proposals on two streams (proposals high priority); %d independent steps "
+                                 "in flight, one library handle each" % LANES},
             "p50_ms": p50, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * K),
             "roofline": roofline, "kernels": kernels}
 
