@@ -130,6 +130,12 @@ extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
     tfrpn_ctx* h = new tfrpn_ctx();
     h->device = device;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    // device counter of the loss reduction (losses.cu): zero between calls, the kernel resets it
+    if (cudaMalloc(&h->ticket, 256) != cudaSuccess || cudaMemset(h->ticket, 0, 256) != cudaSuccess) {
+        cudaError_t e2 = cudaGetLastError();
+        delete h;
+        return cuda_fail(e2, "create: device counter");
+    }
     *out = h;
     return 0;
 }
@@ -142,6 +148,7 @@ extern "C" int tfrpn_destroy(tfrpn_handle h) {
     if (h->dev2) cudaFree(h->dev2);
     if (h->pinned2) cudaFreeHost(h->pinned2);
     if (h->step_pipe) pipe_destroy(h->step_pipe);
+    if (h->ticket) cudaFree(h->ticket);
     delete h;
     return 0;
 }

@@ -56,7 +56,7 @@ unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 ri, wi, ki = H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), H.index("Kernel Name")
 acc = collections.OrderedDict()
 for r in data:
-    name = r[ki].split("(")[0].split("<")[0].replace("void ", "").strip()
+    name = r[ki].split("(")[0].split("<")[0].replace("void ", "").replace("tfrpn::", "").strip()
     acc.setdefault(name, []).append(float(r[ri]) * unit[U[ri]] + float(r[wi]) * unit[U[wi]])
 with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
     json.dump({"source": "profiles/%s_kernels.csv (ncu --set full --clock-control none, per launch)" % tag,
