@@ -124,6 +124,12 @@ TFRPN_API int tfrpn_iou_map(const float* boxes /* (N,4) or (B,N,4) */, int boxes
                   const float* gt_boxes /* (B,G,4) */, int B, int N, int G,
                   float* out /* (B,N,G) */, tfrpn_stream s);
 
+/* Self-test: the IoU kernels divide inter / union with the fast path of div.rn.f32 minus its range check
+ * when every box is in a range where that is exact ("nice" boxes, see common.cuh).  This compares that
+ * sequence with __fdiv_rn on n_pairs pseudo-random operand pairs of its domain and writes the number of
+ * results that differ in any bit (must be 0) to *mismatches_dev (device). */
+TFRPN_API int tfrpn_selftest_division(uint64_t n_pairs, uint64_t seed, uint64_t* mismatches_dev, tfrpn_stream s);
+
 /* ---- get_deltas_from_bboxes: utils/bbox_utils.py:98-124 (no variance scaling) ------ */
 TFRPN_API int tfrpn_encode_deltas(const float* boxes /* (N,4) or (B,N,4) */, int boxes_batched,
                         const float* gt_boxes /* (B,N,4) */, int B, int N,

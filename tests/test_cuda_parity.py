@@ -798,3 +798,32 @@ def test_targets_compact_form_equals_dense(T):
     host = np.empty((B, N, 4), F32)
     assert lib.tfrpn_expand_targets_host(vp(idx_np), vp(rows_np), B, N, TP, None, 0, vp(host)) == 0
     assert bits_equal(host, d_np)
+
+
+def test_range_check_free_division_is_exact(T):
+    """div_rn_inrange (the IoU kernels' division on 'nice' boxes) == __fdiv_rn, bit for bit, on 2^31 operand
+    pairs of its domain, including zero numerators, a == b and extreme mantissas."""
+    from tfrpn import _lib
+    bad = T.torch.ones((1,), dtype=T.torch.int64, device=T.dev)
+    for seed in (1, 2):
+        _lib.check(_lib.load().tfrpn_selftest_division(1 << 30, seed, bad.data_ptr(), T.torch.cuda.current_stream().cuda_stream))
+        assert int(bad.item()) == 0
+
+
+def test_iou_map_nice_and_fallback_paths_agree_with_oracle(T):
+    """K1 takes the range-check-free division when the tile's boxes are 'nice' and the generic path otherwise
+    (a coordinate below 2^-16, a flipped GT box, a zero-area box): both must match the oracle bit for bit."""
+    rng = np.random.default_rng(123)
+    hp = O.get_hyper_params("vgg16")
+    anchors = O.generate_anchors(hp)
+    from tfrpn import synthetic
+    gtb, _ = synthetic.gt_batch(rng, 4, 50)
+    assert bits_equal(T.np(T.bbox.generate_iou_map(T.cu(anchors), T.cu(gtb))), O.generate_iou_map(anchors, gtb))
+    weird = gtb.copy()
+    weird[0, 0] = [1e-7, 0.1, 0.3, 0.4]          # coordinate below 2^-16: not nice
+    weird[1, 1] = [0.5, 0.5, 0.2, 0.2]           # flipped
+    weird[2, 2] = [0.3, 0.3, 0.3, 0.9]           # degenerate but not all-zero
+    assert bits_equal(T.np(T.bbox.generate_iou_map(T.cu(anchors), T.cu(weird))), O.generate_iou_map(anchors, weird))
+    boxes = rand_boxes(rng, 4, 600)
+    boxes[0, 5] = [0.2, 0.2, 0.2, 0.2]           # zero-area box in the tile: generic path, NaN-free here
+    assert bits_equal(T.np(T.bbox.generate_iou_map(T.cu(boxes), T.cu(gtb))), O.generate_iou_map(boxes, gtb))

@@ -85,10 +85,12 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_map_kernel(const float4* __re
     const int n0 = blockIdx.x * IOU_TILE_N;
     const int tn = min(IOU_TILE_N, N - n0);
     const float4* bx = boxes + (long long)b * box_batch_stride + n0;
+    bool nice = true;
     for (int i = threadIdx.x; i < tn; i += IOU_THREADS) {
         float4 v = ldg_f4(bx + i);
         sbox[i] = v;
         sbarea[i] = box_area(v);
+        nice = nice && nice_box(v);
     }
     const float4* gb = gt + (long long)b * G;
     float* o = out + ((long long)b * N + n0) * G;
@@ -98,29 +100,48 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_map_kernel(const float4* __re
         const bool active = r < R;
         const float4 gbx = ldg_f4(gb + g);
         const float ga = box_area(gbx);
-        __syncthreads();
+        // every box of the tile nice and every GT box of the image nice or degenerate (the zero padding)?
+        // (the vote is also the barrier that publishes sbox / sbarea)
+        nice = nice && nice_coords(gbx) && gbx.z >= gbx.x && gbx.w >= gbx.y;
+        const bool all_nice = __syncthreads_and(nice) != 0;
         if (!active) return;
         float* op = o + threadIdx.x;                   // == o + r*G + g
         const int step = R * G;
+        if (all_nice) {   // the division without its range check and the zero test: ~40 % fewer instructions
 #pragma unroll 4
-        for (int n = r; n < tn; n += R, op += step) stg_f1_stream(op, iou_ref(sbox[n], sbarea[n], gbx, ga));
+            for (int n = r; n < tn; n += R, op += step) stg_f1_stream(op, iou_nice(sbox[n], sbarea[n], gbx, ga));
+        } else {
+#pragma unroll 4
+            for (int n = r; n < tn; n += R, op += step) stg_f1_stream(op, iou_ref(sbox[n], sbarea[n], gbx, ga));
+        }
     } else {
         for (int g = threadIdx.x; g < G; g += IOU_THREADS) {
             float4 v = ldg_f4(gb + g);
             sgt[g] = v;
             sgarea[g] = box_area(v);
+            nice = nice && nice_coords(v) && v.z >= v.x && v.w >= v.y;
         }
-        __syncthreads();
+        const bool all_nice = __syncthreads_and(nice) != 0;
         const int total = tn * G;
         const int dn = IOU_THREADS / G, dg = IOU_THREADS - dn * G;
         int e = threadIdx.x;
         int n = e / G, g = e - n * G;
+        if (all_nice) {
 #pragma unroll 4
-        for (; e < total; e += IOU_THREADS) {
-            stg_f1_stream(o + e, iou_ref(sbox[n], sbarea[n], sgt[g], sgarea[g]));
-            n += dn;
-            g += dg;
-            if (g >= G) { g -= G; n += 1; }
+            for (; e < total; e += IOU_THREADS) {
+                stg_f1_stream(o + e, iou_nice(sbox[n], sbarea[n], sgt[g], sgarea[g]));
+                n += dn;
+                g += dg;
+                if (g >= G) { g -= G; n += 1; }
+            }
+        } else {
+#pragma unroll 4
+            for (; e < total; e += IOU_THREADS) {
+                stg_f1_stream(o + e, iou_ref(sbox[n], sbarea[n], sgt[g], sgarea[g]));
+                n += dn;
+                g += dg;
+                if (g >= G) { g -= G; n += 1; }
+            }
         }
     }
 }
@@ -221,6 +242,39 @@ __global__ void __launch_bounds__(EW_THREADS) pad_gt_kernel(const float4* __rest
     }
     out_boxes[i] = bx;
     out_labels[i] = lab;
+}
+
+// Self-test of div_rn_inrange (common.cuh) against __fdiv_rn on pseudo-random operands of its whole domain:
+// b = 2^eb * mb with eb in [-79, 19), a = 0, a = b, or 2^ea * ma with 2^-78 <= a <= b; every eighth pair
+// uses extreme mantissas (all ones / all zeros / one bit) where reciprocal refinement is hardest.
+__global__ void __launch_bounds__(256) selftest_division_kernel(unsigned long long n, unsigned long long seed,
+                                                               unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x51f7u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        uint32_t mb = r.v[0] & 0x7fffffu, ma = r.v[1] & 0x7fffffu;
+        if ((r.v[3] & 7u) == 0u) {
+            const uint32_t pat[4] = {0x7fffffu, 0u, 1u, 0x400000u};
+            mb = pat[(r.v[3] >> 3) & 3u];
+            ma = pat[(r.v[3] >> 5) & 3u];
+        }
+        const int eb = -79 + (int)(r.v[2] % 98u);                              // [-79, 19)
+        const float b = __uint_as_float(((uint32_t)(eb + 127) << 23) | mb);
+        const int lo = -78, span = eb - lo + 1;                                // exponents of a: [-78, eb]
+        float a;
+        const uint32_t kind = (r.v[3] >> 8) & 15u;
+        if (kind == 0u || span <= 0) a = 0.0f;
+        else if (kind == 1u) a = b;
+        else {
+            const int ea = lo + (int)((r.v[2] >> 8) % (uint32_t)span);
+            a = __uint_as_float(((uint32_t)(ea + 127) << 23) | ma);
+            if (a > b) a = b;
+        }
+        const float want = __fdiv_rn(a, b), got = div_rn_inrange(a, b);
+        bad += (__float_as_uint(want) != __float_as_uint(got)) ? 1ull : 0ull;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 static int ew_grid(long long total, int per_thread) {
@@ -363,5 +417,14 @@ extern "C" int tfrpn_pad_gt(const float* flat_boxes, const int32_t* flat_labels,
                                                            flip_or_null, B, G, label_add,
                                                            reinterpret_cast<float4*>(out_boxes), out_labels);
     TFRPN_AFTER_LAUNCH("pad_gt_kernel");
+    return 0;
+}
+
+extern "C" int tfrpn_selftest_division(uint64_t n_pairs, uint64_t seed, uint64_t* mismatches_dev, tfrpn_stream s) {
+    if (!mismatches_dev) return fail(TFRPN_ERR_BAD_ARG, "selftest_division: null pointer");
+    TFRPN_CHECK_CUDA(cudaMemsetAsync(mismatches_dev, 0, sizeof(uint64_t), as_stream(s)));
+    if (n_pairs == 0) return 0;
+    selftest_division_kernel<<<148 * 8, 256, 0, as_stream(s)>>>(n_pairs, seed, reinterpret_cast<unsigned long long*>(mismatches_dev));
+    TFRPN_AFTER_LAUNCH("selftest_division_kernel");
     return 0;
 }

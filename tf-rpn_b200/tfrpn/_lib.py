@@ -64,6 +64,7 @@ PROTOTYPES = {
     "tfrpn_base_anchors_host": (I, [C.POINTER(AnchorCfg), P]),
     "tfrpn_anchors": (I, [C.POINTER(AnchorCfg), P, P]),
     "tfrpn_iou_map": (I, [P, I, P, I, I, I, P, P]),
+    "tfrpn_selftest_division": (I, [C.c_uint64, C.c_uint64, P, P]),
     "tfrpn_encode_deltas": (I, [P, I, P, I, I, P, P]),
     "tfrpn_decode": (I, [P, I, P, P, I, I, I, P, P]),
     "tfrpn_scale_boxes": (I, [P, C.c_int64, C.c_float, C.c_float, I, P, P]),
