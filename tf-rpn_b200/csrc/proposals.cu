@@ -106,6 +106,27 @@ __device__ __forceinline__ bool nms_suppresses(float4 ci, float ai, float4 cj, f
     return 0.0f > t.thr;
 }
 
+// The same decision for SANITISED boxes and a normal positive threshold (t.fast): a box whose area is not
+// > 0 has been replaced by FAR_BOX with area 0 when it was staged, so its intersection with anything is
+// +0 and the area guards leave the loop; the two float pre-filters of iou_exceeds are evaluated without
+// branches and only a quotient within 2^-12 of the threshold (or a degenerate pair) takes the exact path.
+__device__ __forceinline__ bool nms_suppresses_fast(float4 ci, float ai, float4 cj, float aj, const IouThreshold& t) {
+    const float iymin = fmaxf(ci.x, cj.x), ixmin = fmaxf(ci.y, cj.y);
+    const float iymax = fminf(ci.z, cj.z), ixmax = fminf(ci.w, cj.w);
+    const float inter = __fmul_rn(fmaxf(__fsub_rn(iymax, iymin), 0.0f), fmaxf(__fsub_rn(ixmax, ixmin), 0.0f));
+    const float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+    const bool sure = inter > __fmul_rn(t.hi_f, uni);
+    const bool maybe = inter >= __fmul_rn(t.lo_f, uni);
+    if (maybe && !sure) {
+        if (inter == 0.0f) return false;   // degenerate pair (union 0): IOU is 0, and 0 > thr is false for thr > 0
+        const double prod = __dmul_rn(t.mid, (double)uni);
+        const double di = (double)inter;
+        return di > prod || (di == prod && t.tie_up);
+    }
+    return sure;
+}
+#define TFRPN_FAR_BOX make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f)
+
 // descending bitonic sort of PR_THREADS composites, one per thread; thread t ends with rank t.
 // Strides < 32 use shuffles; strides >= 32 go through a double-buffered shared array (1 barrier each).
 __device__ __forceinline__ unsigned long long bitonic_sort_desc(unsigned long long v, unsigned long long* buf) {
@@ -297,8 +318,10 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                     if (p.clip_decoded) raw = clip01(raw);
                 }
                 float4 c = make_float4(fminf(raw.x, raw.z), fminf(raw.y, raw.w), fmaxf(raw.x, raw.z), fmaxf(raw.y, raw.w));
+                float ca = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
+                if (thr.fast && !(ca > 0.0f)) { c = TFRPN_FAR_BOX; ca = 0.0f; }   // see nms_suppresses_fast
                 cbox[tid] = c;
-                carea[tid] = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
+                carea[tid] = ca;
                 alive[tid] = 1u;
             }
             if (tid < NMS_CHUNK * 4) mask32[tid] = 0u;
@@ -310,7 +333,17 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                     const float4 cb = cbox[c];
                     const float ca = carea[c];
                     bool dead = false;
-                    for (int j = part; j < nkept && !dead; j += NMS_PARTS) dead = nms_suppresses(cb, ca, kbox[j], karea[j], thr);
+                    if (thr.fast) {
+                        int j = part;
+                        for (; j + NMS_PARTS < nkept && !dead; j += 2 * NMS_PARTS) {
+                            const bool d0 = nms_suppresses_fast(cb, ca, kbox[j], karea[j], thr);
+                            const bool d1 = nms_suppresses_fast(cb, ca, kbox[j + NMS_PARTS], karea[j + NMS_PARTS], thr);
+                            dead = d0 || d1;
+                        }
+                        if (!dead && j < nkept) dead = nms_suppresses_fast(cb, ca, kbox[j], karea[j], thr);
+                    } else {
+                        for (int j = part; j < nkept && !dead; j += NMS_PARTS) dead = nms_suppresses(cb, ca, kbox[j], karea[j], thr);
+                    }
                     if (dead) alive[c] = 0u;
                 }
             }
@@ -324,7 +357,9 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 for (int e = sub; e < len; e += 16) {
                     const int i = e < iA ? iA : iB;
                     const int j = e < iA ? e : e - iA;
-                    if (alive[i] && alive[j] && nms_suppresses(cbox[j], carea[j], cbox[i], carea[i], thr))
+                    if (alive[i] && alive[j] &&
+                        (thr.fast ? nms_suppresses_fast(cbox[j], carea[j], cbox[i], carea[i], thr)
+                                  : nms_suppresses(cbox[j], carea[j], cbox[i], carea[i], thr)))
                         atomicOr(&mask32[i * 4 + (j >> 5)], 1u << (j & 31));
                 }
             }
