@@ -254,6 +254,11 @@ def run_ours(args):
             step_eager(i)
         return mains[i % LANES]
 
+    def run_steps(first, count):
+        """`count` consecutive steps starting at step index `first` (exactly count steps are enqueued)."""
+        for i in range(first, first + count):
+            run_step(i)
+
     W, K = max(args.warmup, 3), max(args.steps, 1)
     for i in range(W):
         run_step(i)
@@ -272,8 +277,9 @@ def run_ours(args):
     e0.record(cur0)
     for m in mains:
         m.wait_stream(cur0)
-    for i in range(K):
-        run_step(W + i)
+    t_host = time.perf_counter()
+    run_steps(W, K)
+    t_host = time.perf_counter() - t_host   # host time to ENQUEUE the K steps (no synchronisation inside)
     for m in mains:
         cur0.wait_stream(m)
     e1.record(cur0)
@@ -486,7 +492,8 @@ def run_ours(args):
                        "launch": ("eager" if graphs is None else "one CUDA graph per step") +
                                  "; targets || proposals on two streams (proposals high priority); %d independent steps "
                                  "in flight, one library handle each" % LANES},
-            "p50_ms": p50, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * K),
+            "p50_ms": p50, "host_enqueue_ms_per_step": t_host * 1e3 / K, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches_per_step * K),
             "roofline": roofline, "kernels": kernels}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -105,14 +105,26 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_map_kernel(const float4* __re
         nice = nice && nice_coords(gbx) && gbx.z >= gbx.x && gbx.w >= gbx.y;
         const bool all_nice = __syncthreads_and(nice) != 0;
         if (!active) return;
-        float* op = o + threadIdx.x;                   // == o + r*G + g
-        const int step = R * G;
+        // 32-bit element offsets from the CTA's base: one IMAD.WIDE (FMA pipe) per store address instead of
+        // a 64-bit add pair on the ALU pipe, which is the pipe this kernel saturates first (6 FMNMX per element)
+        unsigned e = threadIdx.x;                      // == r*G + g
+        asm("" : "+l"(o));                             // keep the base in one register pair (no re-association)
+        const unsigned step = (unsigned)(R * G);
         if (all_nice) {   // the division without its range check and the zero test: ~40 % fewer instructions
-#pragma unroll 4
-            for (int n = r; n < tn; n += R, op += step) stg_f1_stream(op, iou_nice(sbox[n], sbarea[n], gbx, ga));
+            // two rows per packed FADD2 / FMUL2 / FFMA2 (common.cuh: iou_nice2): fewer issue slots per element
+            const f32x2 ga2 = pack2(ga, ga);
+            int n = r;
+#pragma unroll 2
+            for (; n + R < tn; n += 2 * R, e += 2 * step) {
+                float v0, v1;
+                iou_nice2(sbox[n], sbox[n + R], pack2(sbarea[n], sbarea[n + R]), gbx, ga2, v0, v1);
+                stg_f1_stream(o + e, v0);
+                stg_f1_stream(o + (e + step), v1);
+            }
+            if (n < tn) stg_f1_stream(o + e, iou_nice(sbox[n], sbarea[n], gbx, ga));
         } else {
 #pragma unroll 4
-            for (int n = r; n < tn; n += R, op += step) stg_f1_stream(op, iou_ref(sbox[n], sbarea[n], gbx, ga));
+            for (int n = r; n < tn; n += R, e += step) stg_f1_stream(o + e, iou_ref(sbox[n], sbarea[n], gbx, ga));
         }
     } else {
         for (int g = threadIdx.x; g < G; g += IOU_THREADS) {
