@@ -85,6 +85,8 @@ typedef struct {
     float score_threshold; /* candidates need score > thr; -INFINITY = all  */
     int32_t pad_per_class; /* TF flag; output rows = pad ? min(total, per_class) : total */
     int32_t clip_boxes;    /* clip OUTPUT boxes to [0,1]                     */
+    int32_t pre_nms_topn;  /* > 0: only the top-n scores compete (tf.nn.top_k + gather of predictor.py:58-60
+                              fused in front of the NMS, consumed lazily); 0 = all K boxes */
 } tfrpn_nms_cfg;
 
 typedef struct {

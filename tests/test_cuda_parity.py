@@ -253,6 +253,28 @@ def test_topk_bit_exact(T, B, N, k):
     assert bits_equal(T.np(g), np.take_along_axis(boxes, oi[..., None].astype(np.int64), axis=1))
 
 
+@pytest.mark.parametrize("N,k", [(60000, 100), (131072, 6000), (200003, 3)])
+def test_topk_large_n_prefilter(T, N, k):
+    """N >= 40000 and k <= N/4 goes through the multi-CTA prefilter (histogram select + stable compaction):
+    image 0 random scores, image 1 heavy ties straddling rank k (lower index first must survive the
+    compaction), image 2 ONE tie group larger than the candidate array (falls back to the unfiltered kernel),
+    image 3 negative / zero / -0 scores."""
+    rng = np.random.default_rng(N + k)
+    scores = rng.uniform(0, 1, size=(4, N)).astype(F32)
+    scores[1] = np.round(scores[1] * 200) / 200
+    scores[2] = F32(0.25)
+    scores[2, rng.integers(0, N, size=max(1, k // 2))] = F32(0.75)
+    scores[3] = (rng.integers(-50, 50, size=N).astype(F32)) / F32(16)
+    scores[3, :7] = -0.0
+    boxes = rand_boxes(rng, 4, N)
+    v, i, g = T.bbox.top_k_boxes(T.cu(scores), k, T.cu(boxes))
+    ov, oi = O.top_k(scores, k)
+    assert np.array_equal(T.np(i), oi) and np.array_equal(T.np(v), ov)
+    assert bits_equal(T.np(g), np.take_along_axis(boxes, oi[..., None].astype(np.int64), axis=1))
+    v2, i2 = T.bbox.top_k_boxes(T.cu(scores), k)             # without the gather
+    assert np.array_equal(T.np(i2), oi)
+
+
 def test_topk_ties_and_negative_scores(T):
     rng = np.random.default_rng(0)
     scores = rng.integers(-3, 4, size=(3, 4000)).astype(F32) / F32(4)      # massive ties, +-0
@@ -356,6 +378,25 @@ def test_nms_equal_scores_lower_index_first(T):
     check_nms(T, boxes, scores, max_output_size_per_class=100, max_total_size=100, iou_threshold=0.4)
 
 
+@pytest.mark.parametrize("K,k,sthr", [(5000, 600, float("-inf")), (20000, 6000, float("-inf")), (3000, 3000, 0.2),
+                                      (70000, 2000, float("-inf")), (4000, 50, 0.6)])
+def test_nms_fused_pre_nms_topk(T, K, k, sthr):
+    """pre_nms_topn = tf.nn.top_k + tf.gather (predictor.py:58-60) in front of the NMS: same result as the
+    oracle's top_k -> gather -> combined NMS, keep indices mapped back to the K inputs."""
+    from tfrpn import synthetic
+    rng = np.random.default_rng(K + k)
+    boxes, scores = synthetic.nms_boxes(rng, 2, K, 0.05, 0.4)
+    scores[1, : K // 2] = np.round(scores[1, : K // 2] * 64) / 64          # tie groups straddling the top-k cut
+    kw = dict(max_output_size_per_class=300, max_total_size=300, iou_threshold=0.6, score_threshold=sthr)
+    got = run_nms(T, boxes, scores, pre_nms_topn=k, **kw)
+    v, i = O.top_k(scores, k)
+    sel = np.take_along_axis(boxes, i[..., None].astype(np.int64), axis=1)
+    want = O.combined_non_max_suppression(sel.reshape(2, k, 1, 4), v.reshape(2, k, 1), return_indices=True, **kw)
+    keep = np.where(want[4] >= 0, np.take_along_axis(i, np.maximum(want[4], 0).astype(np.int64), axis=1), -1)
+    assert np.array_equal(got[3], want[3]) and np.array_equal(got[4], keep)
+    assert bits_equal(got[0], want[0]) and bits_equal(got[1], want[1])
+
+
 # ---------------------------------------------------------------- composed proposal stage
 def test_proposals_golden(T, golden):
     hp = T.train.get_hyper_params("vgg16")
@@ -398,6 +439,28 @@ def test_proposals_vs_oracle(T, cfg, B):
     ob, os_, ov, ok = O.generate_proposals(reg, cls, anchors, hp)
     assert np.array_equal(gv, ov) and np.array_equal(gk, ok)
     assert close(gb, ob) and bits_equal(gs, os_)
+
+
+def test_proposals_large_feature_map_prefilter(T):
+    """1333x800 at stride 8: N = 100*167*9 = 150300 anchors, pre-NMS top-6000 -> the fused stage runs on the
+    prefiltered candidates (gathered deltas + anchors, keep indices mapped back through the remap)."""
+    hp = dict(O.get_hyper_params("vgg16"), img_size=(800, 1333), feature_map_shape=(100, 167))
+    anchors = O.generate_anchors(hp)
+    from tfrpn import synthetic
+    rng = np.random.default_rng(99)
+    B = 2
+    reg, cls = synthetic.head_outputs(rng, B, 100, 167, 9)
+    gb, gs, gv, gk = (T.np(x) for x in T.tfrpn.generate_proposals(T.cu(reg), T.cu(cls), T.cu(anchors), hp))
+    ob, os_, ov, ok = O.generate_proposals(reg, cls, anchors, hp)
+    assert np.array_equal(gv, ov) and np.array_equal(gk, ok)
+    assert close(gb, ob) and bits_equal(gs, os_)
+    k = 50
+    boxes, vals, idx = T.tfrpn.predict_top_boxes(T.cu(reg), T.cu(cls), T.cu(anchors), hp, k=k)
+    ts, ti = O.top_k(cls.reshape(B, -1), k)
+    assert np.array_equal(T.np(idx), ti) and bits_equal(T.np(vals), ts)
+    var = np.asarray(hp["variances"], F32)
+    dec = O.get_bboxes_from_deltas(anchors, reg.reshape(B, -1, 4) * var)
+    assert close(T.np(boxes), np.take_along_axis(dec, ti[..., None].astype(np.int64), axis=1))
 
 
 def test_proposals_host_buffers_equal_device_path(T):

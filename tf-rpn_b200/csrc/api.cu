@@ -27,6 +27,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 void count_launch() { ++g_launches; }
 
 size_t targets_workspace_bytes(int B, int N, int G);  // targets.cu
+size_t prefilter_workspace_bytes(int B, int N, int k);  // proposals.cu (0 when the prefilter does not apply)
 
 int sm_count_of(tfrpn_handle h) { return h ? h->sm_count : 148; }
 
@@ -53,6 +54,12 @@ int grow_buffer(char** buf, size_t* have, size_t want, cudaStream_t s, bool pinn
 int ensure_workspace(tfrpn_handle h, size_t bytes, cudaStream_t s, char** out) {
     if (int rc = grow_buffer(&h->ws, &h->ws_bytes, bytes, s, false)) return rc;
     *out = h->ws;
+    return 0;
+}
+
+int ensure_workspace_prop(tfrpn_handle h, size_t bytes, cudaStream_t s, char** out) {
+    if (int rc = grow_buffer(&h->ws_prop, &h->ws_prop_bytes, bytes, s, false)) return rc;
+    *out = h->ws_prop;
     return 0;
 }
 
@@ -143,6 +150,7 @@ extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
 extern "C" int tfrpn_destroy(tfrpn_handle h) {
     if (!h) return 0;
     if (h->ws) cudaFree(h->ws);
+    if (h->ws_prop) cudaFree(h->ws_prop);
     if (h->dev) cudaFree(h->dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->dev2) cudaFree(h->dev2);
@@ -154,15 +162,19 @@ extern "C" int tfrpn_destroy(tfrpn_handle h) {
 }
 
 extern "C" size_t tfrpn_workspace_bytes(int B, int N, int G, int k) {
-    (void)k;  // top-k / NMS work entirely in shared memory
+    // targets scratch + the candidate arrays of the large-N top-k prefilter (small N: top-k / NMS work
+    // entirely in shared memory)
     if (B <= 0 || N <= 0) return 0;
-    return targets_workspace_bytes(B, N, G > 0 ? G : 1);
+    return targets_workspace_bytes(B, N, G > 0 ? G : 1) + prefilter_workspace_bytes(B, N, k);
 }
 
 extern "C" int tfrpn_reserve(tfrpn_handle h, int B, int N, int G, int k) {
     if (!h) return fail(TFRPN_ERR_BAD_ARG, "reserve: null handle");
     char* ws;
-    return ensure_workspace(h, tfrpn_workspace_bytes(B, N, G, k), nullptr, &ws);
+    if (B <= 0 || N <= 0) return 0;
+    if (int rc = ensure_workspace(h, targets_workspace_bytes(B, N, G > 0 ? G : 1), nullptr, &ws)) return rc;
+    const size_t pb = prefilter_workspace_bytes(B, N, k);
+    return pb ? ensure_workspace_prop(h, pb, nullptr, &ws) : 0;
 }
 
 extern "C" int tfrpn_host_alloc(void** out, size_t bytes) {

@@ -17,6 +17,7 @@
 //     predecessor masks inside the round, resolve them in one warp with ballots.
 //   In the fused mode boxes are decoded (+clipped) on the fly, for the examined candidates only.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -57,6 +58,12 @@ struct PropParams {
     float* out_classes;
     int* valid;
     int* keep_idx;
+    // large-N prefilter (launch_prefiltered): per-image entry counts over a compacted candidate array
+    const int* counts;        // entries of image b (null: N)
+    const int* remap;         // (B,N) candidate position -> index in the caller's arrays (null: identity)
+    int anchors_batched;      // MODE_PROPOSALS / predict_topk: anchors are (B,N,4) (gathered candidates)
+    const int* flags;         // (B,) 1 = the candidate array of this image overflowed
+    int flag_mode;            // 0: run every image; 1: skip flagged images; 2: run flagged images only
 };
 
 struct PropShared {
@@ -157,8 +164,14 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     extern __shared__ float4 smem4[];
     __shared__ PropShared sh;
     const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-    const int b = blockIdx.x, N = p.N;
-    const float* scores = p.scores + (long long)b * N;
+    const int b = blockIdx.x;
+    if (p.flag_mode == 1 && p.flags[b] != 0) return;
+    if (p.flag_mode == 2 && p.flags[b] == 0) return;
+    const long long SN = p.N;                          // row stride of scores / reg / remap
+    const int N = p.counts ? p.counts[b] : p.N;        // entries of this image
+    const float* scores = p.scores + (long long)b * SN;
+    const float4* anc = p.anchors + (p.anchors_batched ? (long long)b * SN : 0LL);
+    const int* remap = p.remap ? p.remap + (long long)b * SN : nullptr;
 
     unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(smem4);   // [2 * BATCH]
     uint32_t* sidx = reinterpret_cast<uint32_t*>(sortbuf + 2 * BATCH);            // [BATCH] sorted indices
@@ -277,10 +290,10 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
             if (tid < nb) {
                 const long long o = (long long)b * p.k + lo + tid;
                 p.values[o] = scores[my_i];
-                p.indices[o] = (int)my_i;
+                p.indices[o] = remap ? remap[my_i] : (int)my_i;
                 if (p.gathered) {
                     if (p.reg) {   // predictor.py:55-56 for the selected rows only: decode(anchor, delta * variances)
-                        float4 bx = decode_ref(ldg_f4(p.anchors + my_i), mul4(ldg_f4(p.reg + (long long)b * N + my_i), p.var));
+                        float4 bx = decode_ref(ldg_f4(anc + my_i), mul4(ldg_f4(p.reg + (long long)b * SN + my_i), p.var));
                         p.gathered[o] = p.clip_decoded ? clip01(bx) : bx;
                     } else {
                         p.gathered[o] = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
@@ -298,8 +311,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
             if (tid < NMS_CHUNK && pos + tid < nb) {
                 idx = sidx[pos + tid];
                 if (p.mode == MODE_PROPOSALS) {
-                    d = ldg_f4(p.reg + (long long)b * N + idx);
-                    a = ldg_f4(p.anchors + idx);
+                    d = ldg_f4(p.reg + (long long)b * SN + idx);
+                    a = ldg_f4(anc + idx);
                 } else {
                     a = ldg_f4(p.boxes + (long long)b * p.box_stride + idx);
                 }
@@ -411,7 +424,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 const long long o = (long long)b * p.rows + s;
                 p.out_boxes[o] = p.clip_out ? clip01(raw) : raw;
                 p.out_scores[o] = scores[my_idx];
-                if (p.keep_idx) p.keep_idx[o] = (int)my_idx;
+                if (p.keep_idx) p.keep_idx[o] = remap ? remap[my_idx] : (int)my_idx;
             }
             nkept += sh.nk;
             __syncthreads();
@@ -457,7 +470,279 @@ static size_t prop_smem_bytes(int n_staged, int max_out) {
 }
 constexpr size_t PROP_SMEM_LIMIT = 227 * 1024 - 4096;   // leaves room for the static PropShared
 
+// ------------------------------------------------------------------------------------------------
+// Large-N prefilter.  One CTA per image cannot stream hundreds of thousands of scores several times,
+// so when N is large and only the top k << N ranks can ever be consumed, all SMs first cut every image
+// down to the entries whose key is >= T, the 22-bit prefix of the key at rank k:
+//   pre_hist_kernel pass 0 / 1   2048-bin histograms of key bits [31:21], then [20:10] inside the bin
+//                                that holds rank k (shared-memory bins per slice, flushed with global
+//                                atomics; the last CTA of an image scans them and publishes the digit)
+//   pre_count_kernel             entries >= T per slice; the last CTA turns them into offsets
+//   pre_scatter_kernel           STABLE compaction (ascending original index, so the lower-index-first
+//                                tie rule survives) of scores, original indices and the gathered
+//                                boxes / deltas / anchors into (B, Mcap) arrays
+// proposal_kernel then runs on the compact arrays (counts / remap above).  An image whose candidate set
+// does not fit Mcap (a tie group of thousands of equal keys) is flagged and handled by a second launch
+// of the unfiltered kernel, which returns immediately for every other image.
+// ------------------------------------------------------------------------------------------------
+constexpr int PRE_THREADS = 512;
+constexpr int PRE_WARPS = PRE_THREADS / 32;
+constexpr int PRE_BINS = 2048;
+constexpr int PRE_MIN_N = 40000;      // below this the one-CTA kernel stages every key in shared memory
+constexpr int PRE_SLACK = 8192;       // Mcap = k + PRE_SLACK
+
+struct PreState {
+    unsigned int ticket[3];
+    unsigned int d1, rem1, above1;
+    unsigned int T;
+    unsigned int pad[9];
+};
+
+struct PreParams {
+    const float* scores;
+    int N, k, use_sthr;
+    float sthr;
+    int slices, slice_len, Mcap;
+    unsigned int* hist;        // [B][2][PRE_BINS]
+    PreState* state;           // [B]
+    unsigned int* slice_cnt;   // [B][slices]  counts, then exclusive offsets
+    int* counts;               // [B]
+    int* flags;                // [B]
+    float* cand_scores;        // [B][Mcap]
+    int* remap;                // [B][Mcap]
+    const float4* boxes;       // MODE_TOPK gather source / MODE_NMS input (or null)
+    long long box_stride;
+    float4* cand_boxes;
+    const float4* reg;         // (B,N,4) or null
+    float4* cand_reg;
+    const float4* anchors;     // (N,4)
+    float4* cand_anchors;
+};
+
+// exclusive block scan of one unsigned per thread (PRE_THREADS threads); returns the exclusive prefix,
+// *total gets the block sum
+__device__ __forceinline__ unsigned int pre_block_excl_scan(unsigned int v, unsigned int* wtot, unsigned int* total) {
+    const unsigned int incl = (unsigned int)warp_incl_scan((int)v);
+    if (lane_id() == 31) wtot[warp_id()] = incl;
+    __syncthreads();
+    unsigned int woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < PRE_WARPS; ++w) {
+        const unsigned int t = wtot[w];
+        woff += (w < warp_id()) ? t : 0u;
+        tot += t;
+    }
+    __syncthreads();
+    *total = tot;
+    return woff + incl - v;
+}
+
+__global__ void __launch_bounds__(PRE_THREADS) pre_hist_kernel(PreParams p, int pass) {
+    __shared__ unsigned int sh[PRE_BINS];
+    __shared__ unsigned int wtot[PRE_WARPS];
+    __shared__ unsigned int s_last;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    PreState* st = p.state + b;
+    for (int i = tid; i < PRE_BINS; i += PRE_THREADS) sh[i] = 0u;
+    __syncthreads();
+    const unsigned int d1 = pass ? st->d1 : 0u;
+    const float* sc = p.scores + (long long)b * p.N;
+    const int lo = blockIdx.x * p.slice_len, hi = min(p.N, lo + p.slice_len);
+    for (int i = lo + tid; i < hi; i += PRE_THREADS) {
+        const uint32_t key = score_key(sc[i], p.use_sthr, p.sthr);
+        if (pass == 0) atomicAdd(&sh[key >> 21], 1u);
+        else if ((key >> 21) == d1) atomicAdd(&sh[(key >> 10) & (PRE_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    unsigned int* gh = p.hist + ((long long)b * 2 + pass) * PRE_BINS;
+    for (int i = tid; i < PRE_BINS; i += PRE_THREADS)
+        if (sh[i] != 0u) atomicAdd(&gh[i], sh[i]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&st->ticket[pass], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last == 0u) return;
+    __threadfence();
+    // last CTA of this image: find the bin that holds rank r, scanning from the top (thread 0 = top bins)
+    const unsigned int r = pass ? st->rem1 : (unsigned int)min(p.k, p.N);
+    constexpr int PER = PRE_BINS / PRE_THREADS;   // 4
+    unsigned int c[PER], sum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        c[q] = __ldcg(gh + (PRE_BINS - 1 - (tid * PER + q)));
+        sum += c[q];
+    }
+    unsigned int total;
+    const unsigned int excl = pre_block_excl_scan(sum, wtot, &total);
+    if (excl < r && r <= excl + sum) {
+        unsigned int acc = excl;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            if (acc < r && r <= acc + c[q]) {
+                const unsigned int d = (unsigned int)(PRE_BINS - 1 - (tid * PER + q));
+                if (pass == 0) {
+                    st->d1 = d;
+                    st->rem1 = r - acc;
+                    st->above1 = acc;
+                } else {
+                    st->T = (st->d1 << 21) | (d << 10);
+                    const unsigned int M = st->above1 + acc + c[q];     // entries with key >= T
+                    const bool over = M > (unsigned int)p.Mcap;
+                    p.flags[b] = over ? 1 : 0;
+                    p.counts[b] = over ? 0 : (int)M;
+                }
+            }
+            acc += c[q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PRE_THREADS) pre_count_kernel(PreParams p) {
+    __shared__ unsigned int wtot[PRE_WARPS];
+    __shared__ unsigned int s_last;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (p.flags[b] != 0) return;
+    PreState* st = p.state + b;
+    const unsigned int T = st->T;
+    const float* sc = p.scores + (long long)b * p.N;
+    const int lo = blockIdx.x * p.slice_len, hi = min(p.N, lo + p.slice_len);
+    unsigned int mine = 0;
+    for (int i = lo + tid; i < hi; i += PRE_THREADS) mine += (score_key(sc[i], p.use_sthr, p.sthr) >= T) ? 1u : 0u;
+    unsigned int total;
+    pre_block_excl_scan(mine, wtot, &total);
+    unsigned int* cnt = p.slice_cnt + (long long)b * p.slices;
+    if (tid == 0) {
+        cnt[blockIdx.x] = total;
+        __threadfence();
+        s_last = (atomicAdd(&st->ticket[2], 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last == 0u) return;
+    __threadfence();
+    // last CTA: exclusive scan over the slices (slices <= PRE_THREADS)
+    const unsigned int v = tid < p.slices ? __ldcg(cnt + tid) : 0u;
+    const unsigned int excl = pre_block_excl_scan(v, wtot, &total);
+    if (tid < p.slices) cnt[tid] = excl;
+}
+
+__global__ void __launch_bounds__(PRE_THREADS) pre_scatter_kernel(PreParams p) {
+    __shared__ unsigned int wtot[PRE_WARPS];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = lane_id();
+    if (p.flags[b] != 0) return;
+    const unsigned int T = p.state[b].T;
+    const float* sc = p.scores + (long long)b * p.N;
+    const int lo = blockIdx.x * p.slice_len, hi = min(p.N, lo + p.slice_len);
+    unsigned int running = p.slice_cnt[(long long)b * p.slices + blockIdx.x];
+    const long long ob = (long long)b * p.Mcap;
+    for (int base = lo; base < hi; base += PRE_THREADS) {
+        const int i = base + tid;
+        float s = 0.0f;
+        bool take = false;
+        if (i < hi) {
+            s = sc[i];
+            take = score_key(s, p.use_sthr, p.sthr) >= T;
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, take);
+        if (lane == 0) wtot[warp_id()] = (unsigned int)__popc(bal);
+        __syncthreads();
+        unsigned int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < PRE_WARPS; ++w) {
+            const unsigned int t = wtot[w];
+            woff += (w < warp_id()) ? t : 0u;
+            tot += t;
+        }
+        __syncthreads();
+        if (take) {
+            const long long o = ob + running + woff + __popc(bal & ((1u << lane) - 1u));
+            p.cand_scores[o] = s;
+            p.remap[o] = i;
+            if (p.boxes) p.cand_boxes[o] = ldg_f4(p.boxes + (long long)b * p.box_stride + i);
+            if (p.reg) {
+                p.cand_reg[o] = ldg_f4(p.reg + (long long)b * p.N + i);
+                p.cand_anchors[o] = ldg_f4(p.anchors + i);
+            }
+        }
+        running += tot;
+    }
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static int pre_slices(int B, int N) {
+    int s = (592 + B - 1) / B;                           // ~4 CTAs per SM over the batch
+    s = min(s, (N + 2047) / 2048);                       // at least 2048 entries per slice
+    return max(1, min(s, PRE_THREADS));
+}
+static bool pre_applies(int N, int k) {
+    static const bool off = getenv("TFRPN_NO_PREFILTER") != nullptr;   // A/B switch
+    return !off && k > 0 && N >= PRE_MIN_N && (long long)k * 4 <= N;
+}
+size_t prefilter_workspace_bytes(int B, int N, int k) {
+    if (B <= 0 || !pre_applies(N, k)) return 0;
+    const size_t Mcap = (size_t)min(N, k + PRE_SLACK);
+    size_t b = 0;
+    b += align256((size_t)B * 2 * PRE_BINS * 4 + (size_t)B * sizeof(PreState));   // hist + state (one memset)
+    b += align256((size_t)B * PRE_THREADS * 4);        // slice counts
+    b += align256((size_t)B * 4) * 2;                  // counts, flags
+    b += align256((size_t)B * Mcap * 4) * 2;           // scores, remap
+    b += align256((size_t)B * Mcap * 16) * 2;          // boxes | (reg, anchors)
+    return b + 256;
+}
+
+static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st);
+
+static int launch_prefiltered(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
+    const int N = p.N, Mcap = min(N, p.k + PRE_SLACK);
+    char* ws = nullptr;
+    if (int rc = ensure_workspace_prop(h, prefilter_workspace_bytes(B, N, p.k), st, &ws)) return rc;
+    PreParams q = {};
+    q.scores = p.scores; q.N = N; q.k = p.k; q.use_sthr = p.use_sthr; q.sthr = p.score_threshold;
+    q.slices = pre_slices(B, N);
+    q.slice_len = (N + q.slices - 1) / q.slices;
+    q.Mcap = Mcap;
+    char* c = ws;
+    const size_t zero_bytes = (size_t)B * 2 * PRE_BINS * 4 + (size_t)B * sizeof(PreState);
+    q.hist = reinterpret_cast<unsigned int*>(c);
+    q.state = reinterpret_cast<PreState*>(c + (size_t)B * 2 * PRE_BINS * 4);
+    c += align256(zero_bytes);
+    q.slice_cnt = reinterpret_cast<unsigned int*>(c); c += align256((size_t)B * PRE_THREADS * 4);
+    q.counts = reinterpret_cast<int*>(c); c += align256((size_t)B * 4);
+    q.flags = reinterpret_cast<int*>(c); c += align256((size_t)B * 4);
+    q.cand_scores = reinterpret_cast<float*>(c); c += align256((size_t)B * Mcap * 4);
+    q.remap = reinterpret_cast<int*>(c); c += align256((size_t)B * Mcap * 4);
+    float4* arr0 = reinterpret_cast<float4*>(c); c += align256((size_t)B * Mcap * 16);
+    float4* arr1 = reinterpret_cast<float4*>(c);
+    if (p.reg) { q.reg = p.reg; q.cand_reg = arr0; q.anchors = p.anchors; q.cand_anchors = arr1; }
+    else if (p.boxes) { q.boxes = p.boxes; q.box_stride = p.box_stride; q.cand_boxes = arr0; }
+    TFRPN_CHECK_CUDA(cudaMemsetAsync(q.hist, 0, zero_bytes, st));
+    const dim3 grid(q.slices, B);
+    pre_hist_kernel<<<grid, PRE_THREADS, 0, st>>>(q, 0);
+    TFRPN_AFTER_LAUNCH("pre_hist_kernel");
+    pre_hist_kernel<<<grid, PRE_THREADS, 0, st>>>(q, 1);
+    TFRPN_AFTER_LAUNCH("pre_hist_kernel");
+    pre_count_kernel<<<grid, PRE_THREADS, 0, st>>>(q);
+    TFRPN_AFTER_LAUNCH("pre_count_kernel");
+    pre_scatter_kernel<<<grid, PRE_THREADS, 0, st>>>(q);
+    TFRPN_AFTER_LAUNCH("pre_scatter_kernel");
+    // the one-CTA-per-image kernel on the compact arrays ...
+    PropParams c1 = p;
+    c1.N = Mcap; c1.scores = q.cand_scores; c1.counts = q.counts; c1.remap = q.remap;
+    c1.flags = q.flags; c1.flag_mode = 1;
+    if (p.reg) { c1.reg = arr0; c1.anchors = arr1; c1.anchors_batched = 1; }
+    else if (p.boxes) { c1.boxes = arr0; c1.box_stride = Mcap; }
+    if (int rc = launch_one(h, c1, B, st)) return rc;
+    // ... and the unfiltered kernel for the images whose candidates did not fit (normally none)
+    PropParams c2 = p;
+    c2.flags = q.flags; c2.flag_mode = 2;
+    return launch_one(h, c2, B, st);
+}
+
 static int launch(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
+    if (h && pre_applies(p.N, p.k)) return launch_prefiltered(h, p, B, st);
+    return launch_one(h, p, B, st);
+}
+
+static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
     p.mo_pad = (p.max_out + 3) & ~3;
     p.staged = prop_smem_bytes(p.N, p.max_out) <= PROP_SMEM_LIMIT ? 1 : 0;
     const size_t smem = prop_smem_bytes(p.staged ? p.N : 0, p.max_out);
@@ -528,7 +813,8 @@ extern "C" int tfrpn_nms(tfrpn_handle h, const float* boxes, const float* scores
     if (!aligned16(boxes) || !aligned16(out_boxes)) return fail(TFRPN_ERR_MISALIGNED, "nms: boxes must be 16-byte aligned");
     if (B == 0) return 0;
     PropParams p = {};
-    p.mode = MODE_NMS; p.N = K; p.k = K; p.scores = scores;
+    if (cfg->pre_nms_topn < 0) return fail(TFRPN_ERR_BAD_ARG, "nms: pre_nms_topn must be >= 0");
+    p.mode = MODE_NMS; p.N = K; p.k = cfg->pre_nms_topn > 0 ? min(K, cfg->pre_nms_topn) : K; p.scores = scores;
     p.use_sthr = !(cfg->score_threshold == -INFINITY);
     p.score_threshold = cfg->score_threshold;
     p.boxes = reinterpret_cast<const float4*>(boxes); p.box_stride = K;

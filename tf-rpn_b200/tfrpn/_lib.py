@@ -30,7 +30,7 @@ class TargetDebug(C.Structure):
 class NmsCfg(C.Structure):
     _fields_ = [("max_output_size_per_class", C.c_int32), ("max_total_size", C.c_int32),
                 ("iou_threshold", C.c_float), ("score_threshold", C.c_float),
-                ("pad_per_class", C.c_int32), ("clip_boxes", C.c_int32)]
+                ("pad_per_class", C.c_int32), ("clip_boxes", C.c_int32), ("pre_nms_topn", C.c_int32)]
 
 
 class ProposalCfg(C.Structure):

@@ -64,9 +64,11 @@ def non_max_suppression(pred_bboxes, pred_labels, **kwargs):
     pred_bboxes (B, K, 1, 4), pred_labels (B, K, 1); kwargs are TF's: max_output_size_per_class,
     max_total_size, iou_threshold=0.5, score_threshold=-inf, pad_per_class=False, clip_boxes=True.
     Extra kwarg ``return_indices=True`` appends the kept indices (B, rows) int32, -1 padded.
+    Extra kwarg ``pre_nms_topn=k`` lets only the k best scores compete: the tf.nn.top_k + tf.gather of
+    predictor.py:58-60 fused in front of the NMS (same result as calling them first, but consumed lazily).
     """
     known = {"max_output_size_per_class", "max_total_size", "iou_threshold", "score_threshold",
-             "pad_per_class", "clip_boxes", "name", "return_indices"}
+             "pad_per_class", "clip_boxes", "name", "return_indices", "pre_nms_topn"}
     unknown = set(kwargs) - known
     if unknown:
         raise TypeError("non_max_suppression() got unexpected keyword arguments %s" % sorted(unknown))
@@ -84,7 +86,8 @@ def non_max_suppression(pred_bboxes, pred_labels, **kwargs):
         raise ValueError("pred_bboxes %s and pred_labels %s disagree" % (tuple(boxes.shape), tuple(scores.shape)))
     cfg = _lib.NmsCfg(int(kwargs["max_output_size_per_class"]), int(kwargs["max_total_size"]),
                       float(kwargs.get("iou_threshold", 0.5)), float(kwargs.get("score_threshold", float("-inf"))),
-                      int(bool(kwargs.get("pad_per_class", False))), int(bool(kwargs.get("clip_boxes", True))))
+                      int(bool(kwargs.get("pad_per_class", False))), int(bool(kwargs.get("clip_boxes", True))),
+                      int(kwargs.get("pre_nms_topn") or 0))
     rows = min(cfg.max_total_size, cfg.max_output_size_per_class) if cfg.pad_per_class else cfg.max_total_size
     dev = boxes.device
     nb = torch.empty((B, rows, 4), dtype=F32, device=dev)
