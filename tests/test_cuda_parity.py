@@ -397,6 +397,25 @@ def test_nms_fused_pre_nms_topk(T, K, k, sthr):
     assert bits_equal(got[0], want[0]) and bits_equal(got[1], want[1])
 
 
+def test_nms_large_k_truncated_candidates(T):
+    """NMS over all K = 90000 boxes: the prefilter keeps the top ~6144 ranks; image 0 finishes inside them,
+    image 1 (tiny disjoint boxes on a grid: nothing is ever suppressed, max_output 300 reached quickly) too,
+    image 2 has only 40 boxes above the score threshold among its candidates' scores but all its boxes are
+    near-duplicates, so the candidates run out before 300 are kept and the unfiltered kernel redoes it."""
+    from tfrpn import synthetic
+    rng = np.random.default_rng(90000)
+    K = 90000
+    boxes, scores = synthetic.nms_boxes(rng, 3, K, 0.05, 0.4)
+    g = np.arange(K)
+    y, x = (g // 300) / F32(300), (g % 300) / F32(300)
+    boxes[1] = np.stack([y, x, y + F32(0.002), x + F32(0.002)], -1).astype(F32)
+    c = rng.uniform(0.49, 0.51, size=(K, 2)); sz = rng.uniform(0.3, 0.31, size=(K, 2))
+    boxes[2] = np.concatenate([c - sz / 2, c + sz / 2], -1).astype(F32)
+    check_nms(T, boxes, scores, max_output_size_per_class=300, max_total_size=300, iou_threshold=0.7)
+    check_nms(T, boxes, scores, max_output_size_per_class=300, max_total_size=300, iou_threshold=0.7,
+              score_threshold=0.999)
+
+
 # ---------------------------------------------------------------- composed proposal stage
 def test_proposals_golden(T, golden):
     hp = T.train.get_hyper_params("vgg16")

@@ -64,6 +64,8 @@ struct PropParams {
     int anchors_batched;      // MODE_PROPOSALS / predict_topk: anchors are (B,N,4) (gathered candidates)
     const int* flags;         // (B,) 1 = the candidate array of this image overflowed
     int flag_mode;            // 0: run every image; 1: skip flagged images; 2: run flagged images only
+    int* flags_out;           // NMS over a TRUNCATED candidate set: raise flags[b] when the candidates ran out
+    int full_n;               //   before max_out boxes were kept and the image has more than its candidates
 };
 
 struct PropShared {
@@ -432,6 +434,10 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
         if (nkept >= p.max_out) break;
     }
     if (p.mode == MODE_TOPK) return;
+    if (p.flags_out && nkept < p.max_out && N < p.full_n) {   // the unfiltered kernel redoes this image
+        if (tid == 0) p.flags_out[b] = 1;
+        return;
+    }
     // zero padding (TF pads boxes/scores/classes with 0); keep_idx pads with -1
     for (int rnk = tid; rnk < p.rows; rnk += PR_THREADS) {
         const long long o = (long long)b * p.rows + rnk;
@@ -490,6 +496,11 @@ constexpr int PRE_WARPS = PRE_THREADS / 32;
 constexpr int PRE_BINS = 2048;
 constexpr int PRE_MIN_N = 40000;      // below this the one-CTA kernel stages every key in shared memory
 constexpr int PRE_SLACK = 8192;       // Mcap = k + PRE_SLACK
+// NMS over "all" K boxes (or a very large pre-NMS k) rarely looks past the first few thousand ranks: the
+// prefilter then keeps only the top PRE_NMS_CAP ranks, and an image whose NMS runs out of candidates
+// before max_out boxes are kept raises its flag and is redone by the unfiltered kernel.
+constexpr int PRE_NMS_CAP = 6144;
+constexpr int PRE_NMS_CAP_MAX_OUT = 384;
 
 struct PreState {
     unsigned int ticket[3];
@@ -677,7 +688,13 @@ static bool pre_applies(int N, int k) {
     static const bool off = getenv("TFRPN_NO_PREFILTER") != nullptr;   // A/B switch
     return !off && k > 0 && N >= PRE_MIN_N && (long long)k * 4 <= N;
 }
+static size_t prefilter_bytes_for(int B, int N, int k);
 size_t prefilter_workspace_bytes(int B, int N, int k) {
+    if (k <= 0) k = N;
+    const size_t a = prefilter_bytes_for(B, N, k), b = prefilter_bytes_for(B, N, min(k, PRE_NMS_CAP));
+    return a > b ? a : b;
+}
+static size_t prefilter_bytes_for(int B, int N, int k) {
     if (B <= 0 || !pre_applies(N, k)) return 0;
     const size_t Mcap = (size_t)min(N, k + PRE_SLACK);
     size_t b = 0;
@@ -691,12 +708,13 @@ size_t prefilter_workspace_bytes(int B, int N, int k) {
 
 static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st);
 
-static int launch_prefiltered(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
-    const int N = p.N, Mcap = min(N, p.k + PRE_SLACK);
+static int launch_prefiltered(tfrpn_handle h, PropParams& p, int k_eff, int B, cudaStream_t st) {
+    const int N = p.N, Mcap = min(N, k_eff + PRE_SLACK);
+    const bool truncated = k_eff < p.k;
     char* ws = nullptr;
-    if (int rc = ensure_workspace_prop(h, prefilter_workspace_bytes(B, N, p.k), st, &ws)) return rc;
+    if (int rc = ensure_workspace_prop(h, prefilter_bytes_for(B, N, k_eff), st, &ws)) return rc;
     PreParams q = {};
-    q.scores = p.scores; q.N = N; q.k = p.k; q.use_sthr = p.use_sthr; q.sthr = p.score_threshold;
+    q.scores = p.scores; q.N = N; q.k = k_eff; q.use_sthr = p.use_sthr; q.sthr = p.score_threshold;
     q.slices = pre_slices(B, N);
     q.slice_len = (N + q.slices - 1) / q.slices;
     q.Mcap = Mcap;
@@ -728,6 +746,11 @@ static int launch_prefiltered(tfrpn_handle h, PropParams& p, int B, cudaStream_t
     PropParams c1 = p;
     c1.N = Mcap; c1.scores = q.cand_scores; c1.counts = q.counts; c1.remap = q.remap;
     c1.flags = q.flags; c1.flag_mode = 1;
+    if (truncated) {   // every candidate may be consumed, up to the caller's k; full_n = ranks an unfiltered run may use
+        c1.k = min(Mcap, p.k);
+        c1.flags_out = q.flags;
+        c1.full_n = min(N, p.k);
+    }
     if (p.reg) { c1.reg = arr0; c1.anchors = arr1; c1.anchors_batched = 1; }
     else if (p.boxes) { c1.boxes = arr0; c1.box_stride = Mcap; }
     if (int rc = launch_one(h, c1, B, st)) return rc;
@@ -738,7 +761,9 @@ static int launch_prefiltered(tfrpn_handle h, PropParams& p, int B, cudaStream_t
 }
 
 static int launch(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
-    if (h && pre_applies(p.N, p.k)) return launch_prefiltered(h, p, B, st);
+    int k_eff = p.k;
+    if (p.mode != MODE_TOPK && p.max_out <= PRE_NMS_CAP_MAX_OUT) k_eff = min(p.k, PRE_NMS_CAP);
+    if (h && pre_applies(p.N, k_eff)) return launch_prefiltered(h, p, k_eff, B, st);
     return launch_one(h, p, B, st);
 }
 
