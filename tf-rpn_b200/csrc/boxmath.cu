@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(EW_THREADS) pad_gt_kernel(const float4* __rest
     out_labels[i] = lab;
 }
 
-// Self-test of div_rn_inrange (common.cuh) against __fdiv_rn on pseudo-random operands of its whole domain:
+// Self-test of div_rn_inrange and its packed form div2_rn_inrange (common.cuh) against __fdiv_rn on pseudo-random operands of its whole domain:
 // b = 2^eb * mb with eb in [-79, 19), a = 0, a = b, or 2^ea * ma with 2^-78 <= a <= b; every eighth pair
 // uses extreme mantissas (all ones / all zeros / one bit) where reciprocal refinement is hardest.
 __global__ void __launch_bounds__(256) selftest_division_kernel(unsigned long long n, unsigned long long seed,
@@ -285,6 +285,10 @@ __global__ void __launch_bounds__(256) selftest_division_kernel(unsigned long lo
         }
         const float want = __fdiv_rn(a, b), got = div_rn_inrange(a, b);
         bad += (__float_as_uint(want) != __float_as_uint(got)) ? 1ull : 0ull;
+        // the packed form (FFMA2), this pair in one half and the pair (b, b) in the other
+        float p0, p1;
+        unpack2(div2_rn_inrange(pack2(a, b), pack2(-b, -b)), p0, p1);
+        bad += (__float_as_uint(want) != __float_as_uint(p0) || p1 != 1.0f) ? 1ull : 0ull;
     }
     if (bad) atomicAdd(mismatches, bad);
 }

@@ -38,6 +38,10 @@ def main():
         gtb, gtl = synthetic.gt_batch(rng, B, 50)
         reg, cls = synthetic.head_outputs(rng, B, 31, 31, 9)
         sets.append([torch.from_numpy(a).to(dev) for a in (gtb, gtl, reg, cls)])
+    big = None
+    if args.extras:   # C5-style input for the large-N prefilter: 8 images x 200k boxes
+        bx, sc = synthetic.nms_boxes(rng, 8, 200000)
+        big = (torch.from_numpy(bx).to(dev).reshape(8, -1, 1, 4), torch.from_numpy(sc).to(dev).reshape(8, -1, 1))
     for i in range(args.steps):
         gtb, gtl, reg, cls = sets[i % 3]
         deltas, labels = train_utils.calculate_rpn_actual_outputs(anchors, gtb, gtl, hp, seed=1, offset=i)
@@ -50,6 +54,8 @@ def main():
             bbox_utils.top_k_boxes(cls.reshape(B, -1), 6000, boxes)
             train_utils.rpn_losses(deltas, reg, labels, cls, with_grads=True)
             tfrpn.predict_top_boxes(reg, cls, anchors, hp, k=10)
+            bbox_utils.non_max_suppression(big[0], big[1], max_output_size_per_class=300, max_total_size=300,
+                                           iou_threshold=0.7, pre_nms_topn=6000)
     torch.cuda.synchronize()
     print("done", tfrpn._lib.launch_count(), "launches")
 
