@@ -303,6 +303,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         lat.append(a.elapsed_time(b))
     p50 = float(np.median(lat))
+    p90 = float(np.percentile(lat, 90))
 
     # ---- per-kernel device time, live (library tracing hooks, eager launches, rotating sets) ----
     hbm_peak, peak_src = peaks()
@@ -497,7 +498,7 @@ def run_ours(args):
                        "launch": ("eager" if graphs is None else "one CUDA graph per step") +
                                  "; targets || proposals on two streams (proposals high priority); %d independent steps "
                                  "in flight, one library handle each" % LANES},
-            "p50_ms": p50, "host_enqueue_ms_per_step": t_host * 1e3 / K, "clocks": clocks, "e2e": e2e,
+            "p50_ms": p50, "p90_ms": p90, "host_enqueue_ms_per_step": t_host * 1e3 / K, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches_per_step * K),
             "roofline": roofline, "kernels": kernels}
 
