@@ -3,11 +3,14 @@
 proposals, C5 NMS / top-k stress at K = 10k..500k), device-resident, next to the CPU restatement on
 the host cores.  Each GPU result of the run is also compared with the oracle on a sample.
 
-    python tools/sweep.py [--out profiles/rNN_sweep.json] [--quick]
+    python tests/sweep_configs.py [--out profiles/rNN_sweep.json] [--quick]
 
 Timing: CUDA events around `reps` back-to-back steps over rotating input sets (so that inputs do not
 sit in L2 between steps); the CPU column is oracle/rpn_oracle.c with OpenMP over images on all host
 threads, timed on a bounded sample (kind "port": the reference is TF 2.0 Python, not installable).
+The script lives under tests/ (pytest does not collect it) because it links oracle/ -- as the in-run
+checker and as the timed CPU baseline, never on the GPU path; nothing outside tests/, bench.py's CPU legs
+and __graft_entry__.smoke() touches the oracle.
 """
 import argparse
 import ctypes as C
