@@ -334,7 +334,14 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch", {})
+            tj = json.load(f)
+        traffic = dict(tj.get("dram_bytes_per_launch", {}))
+        # one kernel name covers several launch shapes / modes: take the captured group whose duration is
+        # closest to the launch timed here
+        for k, us in kern.items():
+            gs = tj.get("groups", {}).get(k)
+            if gs:
+                traffic[k] = min(gs.values(), key=lambda g: abs(g["avg_us"] - us))["dram_bytes"]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic.get(dominant), "us_per_launch": dom_us,
                 "algorithmic_bytes": alg[dominant], "peak_source": peak_src,

@@ -52,6 +52,7 @@ with open(os.path.join(ROOT, "profiles", tag + "_kernels.csv"), "w") as f:
         w.writerow([r[i][:90] for _, i in idx])
 # DRAM bytes per launch (read + write), averaged per kernel -> profiles/traffic.json (bench.py's roofline.traffic)
 import json
+import math
 unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 ri, wi, ki = H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), H.index("Kernel Name")
 gi, si, di = H.index("launch__grid_size"), H.index("launch__shared_mem_per_block_dynamic"), H.index("gpu__time_duration.sum")
@@ -61,10 +62,12 @@ gi, si, di = H.index("launch__grid_size"), H.index("launch__shared_mem_per_block
 acc = collections.OrderedDict()
 for r in data:
     name = r[ki].split("(")[0].split("<")[0].replace("void ", "").replace("tfrpn::", "").strip()
-    grp = "grid=%s smem=%s%s" % (r[gi], r[si], U[si])
+    us = float(r[di]) * {"us": 1.0, "ns": 1e-3, "ms": 1e3}.get(U[di], 1.0)
+    # launches of one shape can still be different modes (top-k of 10 vs of 6000): half-octave duration buckets
+    grp = "grid=%s smem=%s%s ~%dus" % (r[gi], r[si], U[si], round(2 ** (round(math.log2(max(us, 0.5)) * 2) / 2)))
     g = acc.setdefault(name, collections.OrderedDict()).setdefault(grp, {"bytes": [], "us": []})
     g["bytes"].append(float(r[ri]) * unit[U[ri]] + float(r[wi]) * unit[U[wi]])
-    g["us"].append(float(r[di]) * {"us": 1.0, "ns": 1e-3, "ms": 1e3}.get(U[di], 1.0))
+    g["us"].append(us)
 mean = lambda v: sum(v) / len(v)
 per_name, groups = collections.OrderedDict(), collections.OrderedDict()
 for name, gs in acc.items():
