@@ -483,7 +483,7 @@ constexpr size_t PROP_SMEM_LIMIT = 227 * 1024 - 4096;   // leaves room for the s
 //   pre_hist_kernel pass 0 / 1   2048-bin histograms of key bits [31:21], then [20:10] inside the bin
 //                                that holds rank k (shared-memory bins per slice, flushed with global
 //                                atomics; the last CTA of an image scans them and publishes the digit)
-//   pre_count_kernel             entries >= T per slice; the last CTA turns them into offsets
+//   pre_count_kernel             entries >= T per warp sub-slice; the last CTA turns them into offsets
 //   pre_scatter_kernel           STABLE compaction (ascending original index, so the lower-index-first
 //                                tie rule survives) of scores, original indices and the gathered
 //                                boxes / deltas / anchors into (B, Mcap) arrays
@@ -516,7 +516,7 @@ struct PreParams {
     int slices, slice_len, Mcap;
     unsigned int* hist;        // [B][2][PRE_BINS]
     PreState* state;           // [B]
-    unsigned int* slice_cnt;   // [B][slices]  counts, then exclusive offsets
+    unsigned int* slice_cnt;   // [B][slices][PRE_WARPS]  per-warp counts, then exclusive offsets
     int* counts;               // [B]
     int* flags;                // [B]
     float* cand_scores;        // [B][Mcap]
@@ -608,45 +608,65 @@ __global__ void __launch_bounds__(PRE_THREADS) pre_hist_kernel(PreParams p, int 
     }
 }
 
+// count / scatter work on per-WARP sub-slices (warp w of slice s owns entries [lo + w*sub, lo + (w+1)*sub)), so
+// neither needs a block-wide scan per chunk: a warp counts with ballots, and scatters from its own offset.
+__device__ __forceinline__ void pre_warp_range(const PreParams& p, int slice, int& lo, int& hi) {
+    const int slo = slice * p.slice_len, shi = min(p.N, slo + p.slice_len);
+    const int sub = (((p.slice_len + PRE_WARPS - 1) / PRE_WARPS) + 31) & ~31;
+    lo = min(shi, slo + warp_id() * sub);
+    hi = min(shi, lo + sub);
+}
+
 __global__ void __launch_bounds__(PRE_THREADS) pre_count_kernel(PreParams p) {
     __shared__ unsigned int wtot[PRE_WARPS];
     __shared__ unsigned int s_last;
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = lane_id();
     if (p.flags[b] != 0) return;
     PreState* st = p.state + b;
     const unsigned int T = st->T;
     const float* sc = p.scores + (long long)b * p.N;
-    const int lo = blockIdx.x * p.slice_len, hi = min(p.N, lo + p.slice_len);
+    int lo, hi;
+    pre_warp_range(p, blockIdx.x, lo, hi);
     unsigned int mine = 0;
-    for (int i = lo + tid; i < hi; i += PRE_THREADS) mine += (score_key(sc[i], p.use_sthr, p.sthr) >= T) ? 1u : 0u;
-    unsigned int total;
-    pre_block_excl_scan(mine, wtot, &total);
-    unsigned int* cnt = p.slice_cnt + (long long)b * p.slices;
-    if (tid == 0) {
-        cnt[blockIdx.x] = total;
-        __threadfence();
-        s_last = (atomicAdd(&st->ticket[2], 1u) == gridDim.x - 1) ? 1u : 0u;
-    }
+    for (int i = lo + lane; i < hi; i += 32) mine += (score_key(sc[i], p.use_sthr, p.sthr) >= T) ? 1u : 0u;
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    unsigned int* cnt = p.slice_cnt + (long long)b * p.slices * PRE_WARPS;
+    if (lane == 0) cnt[blockIdx.x * PRE_WARPS + warp_id()] = mine;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&st->ticket[2], 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
     if (s_last == 0u) return;
     __threadfence();
-    // last CTA: exclusive scan over the slices (slices <= PRE_THREADS)
-    const unsigned int v = tid < p.slices ? __ldcg(cnt + tid) : 0u;
-    const unsigned int excl = pre_block_excl_scan(v, wtot, &total);
-    if (tid < p.slices) cnt[tid] = excl;
+    // last CTA: exclusive scan over all sub-slices; thread t owns the PRE_WARPS entries of slice t
+    unsigned int v[PRE_WARPS], sum = 0;
+#pragma unroll
+    for (int w = 0; w < PRE_WARPS; ++w) {
+        v[w] = tid < p.slices ? __ldcg(cnt + tid * PRE_WARPS + w) : 0u;
+        sum += v[w];
+    }
+    unsigned int total;
+    unsigned int run = pre_block_excl_scan(sum, wtot, &total);
+    if (tid < p.slices) {
+#pragma unroll
+        for (int w = 0; w < PRE_WARPS; ++w) {
+            cnt[tid * PRE_WARPS + w] = run;
+            run += v[w];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(PRE_THREADS) pre_scatter_kernel(PreParams p) {
-    __shared__ unsigned int wtot[PRE_WARPS];
-    const int b = blockIdx.y, tid = threadIdx.x, lane = lane_id();
+    const int b = blockIdx.y, lane = lane_id();
     if (p.flags[b] != 0) return;
     const unsigned int T = p.state[b].T;
     const float* sc = p.scores + (long long)b * p.N;
-    const int lo = blockIdx.x * p.slice_len, hi = min(p.N, lo + p.slice_len);
-    unsigned int running = p.slice_cnt[(long long)b * p.slices + blockIdx.x];
+    int lo, hi;
+    pre_warp_range(p, blockIdx.x, lo, hi);
+    unsigned int running = p.slice_cnt[((long long)b * p.slices + blockIdx.x) * PRE_WARPS + warp_id()];
     const long long ob = (long long)b * p.Mcap;
-    for (int base = lo; base < hi; base += PRE_THREADS) {
-        const int i = base + tid;
+    for (int base = lo; base < hi; base += 32) {
+        const int i = base + lane;
         float s = 0.0f;
         bool take = false;
         if (i < hi) {
@@ -654,18 +674,8 @@ __global__ void __launch_bounds__(PRE_THREADS) pre_scatter_kernel(PreParams p) {
             take = score_key(s, p.use_sthr, p.sthr) >= T;
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, take);
-        if (lane == 0) wtot[warp_id()] = (unsigned int)__popc(bal);
-        __syncthreads();
-        unsigned int woff = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < PRE_WARPS; ++w) {
-            const unsigned int t = wtot[w];
-            woff += (w < warp_id()) ? t : 0u;
-            tot += t;
-        }
-        __syncthreads();
         if (take) {
-            const long long o = ob + running + woff + __popc(bal & ((1u << lane) - 1u));
+            const long long o = ob + running + __popc(bal & ((1u << lane) - 1u));
             p.cand_scores[o] = s;
             p.remap[o] = i;
             if (p.boxes) p.cand_boxes[o] = ldg_f4(p.boxes + (long long)b * p.box_stride + i);
@@ -674,7 +684,7 @@ __global__ void __launch_bounds__(PRE_THREADS) pre_scatter_kernel(PreParams p) {
                 p.cand_anchors[o] = ldg_f4(p.anchors + i);
             }
         }
-        running += tot;
+        running += __popc(bal);
     }
 }
 
@@ -699,7 +709,7 @@ static size_t prefilter_bytes_for(int B, int N, int k) {
     const size_t Mcap = (size_t)min(N, k + PRE_SLACK);
     size_t b = 0;
     b += align256((size_t)B * 2 * PRE_BINS * 4 + (size_t)B * sizeof(PreState));   // hist + state (one memset)
-    b += align256((size_t)B * PRE_THREADS * 4);        // slice counts
+    b += align256((size_t)B * PRE_THREADS * PRE_WARPS * 4);   // sub-slice counts / offsets
     b += align256((size_t)B * 4) * 2;                  // counts, flags
     b += align256((size_t)B * Mcap * 4) * 2;           // scores, remap
     b += align256((size_t)B * Mcap * 16) * 2;          // boxes | (reg, anchors)
@@ -723,7 +733,7 @@ static int launch_prefiltered(tfrpn_handle h, PropParams& p, int k_eff, int B, c
     q.hist = reinterpret_cast<unsigned int*>(c);
     q.state = reinterpret_cast<PreState*>(c + (size_t)B * 2 * PRE_BINS * 4);
     c += align256(zero_bytes);
-    q.slice_cnt = reinterpret_cast<unsigned int*>(c); c += align256((size_t)B * PRE_THREADS * 4);
+    q.slice_cnt = reinterpret_cast<unsigned int*>(c); c += align256((size_t)B * PRE_THREADS * PRE_WARPS * 4);
     q.counts = reinterpret_cast<int*>(c); c += align256((size_t)B * 4);
     q.flags = reinterpret_cast<int*>(c); c += align256((size_t)B * 4);
     q.cand_scores = reinterpret_cast<float*>(c); c += align256((size_t)B * Mcap * 4);
