@@ -158,6 +158,58 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_map_kernel(const float4* __re
     }
 }
 
+// Even G (<= 256): a thread owns TWO adjacent GT columns and walks the rows, so one staged box serves two map
+// entries (one LDS.128 + one LDS per pair instead of per entry), both quotients come out of one packed
+// division, and the pair leaves as one 8-byte streaming store (row starts are 8-byte aligned when G is even):
+// half the load / store instructions of the one-column kernel.  IoU is symmetric in its two boxes down to the
+// bits (fmax / fmin / fadd commute), so iou_nice2 is called with the roles of box and GT swapped.
+__global__ void __launch_bounds__(IOU_THREADS) iou_map_pairs_kernel(const float4* __restrict__ boxes,
+                                                                    long long box_batch_stride,
+                                                                    const float4* __restrict__ gt, int N, int G,
+                                                                    float* __restrict__ out) {
+    __shared__ float4 sbox[IOU_TILE_N];
+    __shared__ float sbarea[IOU_TILE_N];
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * IOU_TILE_N;
+    const int tn = min(IOU_TILE_N, N - n0);
+    const float4* bx = boxes + (long long)b * box_batch_stride + n0;
+    bool nice = true;
+    for (int i = threadIdx.x; i < tn; i += IOU_THREADS) {
+        float4 v = ldg_f4(bx + i);
+        sbox[i] = v;
+        sbarea[i] = box_area(v);
+        nice = nice && nice_box(v);
+    }
+    const int H = G >> 1;                              // column pairs per row
+    const int R = IOU_THREADS / H;                     // rows per iteration
+    const int r = threadIdx.x / H, h = threadIdx.x - r * H;
+    const bool active = r < R;
+    const float4* gb = gt + (long long)b * G;
+    const float4 g0 = ldg_f4(gb + 2 * h), g1 = ldg_f4(gb + 2 * h + 1);
+    const float ga0 = box_area(g0), ga1 = box_area(g1);
+    nice = nice && nice_coords(g0) && g0.z >= g0.x && g0.w >= g0.y && nice_coords(g1) && g1.z >= g1.x && g1.w >= g1.y;
+    const bool all_nice = __syncthreads_and(nice) != 0;   // also publishes sbox / sbarea
+    if (!active) return;
+    float2* o2 = reinterpret_cast<float2*>(out + ((long long)b * N + n0) * G);
+    asm("" : "+l"(o2));                                // keep the base in one register pair (IMAD.WIDE addressing)
+    unsigned e = threadIdx.x;                          // == r*H + h, in float2 units
+    const unsigned step = (unsigned)(R * H);
+    if (all_nice) {
+        const f32x2 ga2 = pack2(ga0, ga1);
+#pragma unroll 2
+        for (int n = r; n < tn; n += R, e += step) {
+            const float ba = sbarea[n];
+            float v0, v1;
+            iou_nice2(g0, g1, ga2, sbox[n], pack2(ba, ba), v0, v1);
+            stg_f2_stream(o2 + e, v0, v1);
+        }
+    } else {
+#pragma unroll 2
+        for (int n = r; n < tn; n += R, e += step)
+            stg_f2_stream(o2 + e, iou_ref(sbox[n], sbarea[n], g0, ga0), iou_ref(sbox[n], sbarea[n], g1, ga1));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Elementwise kernels: one float4 box per element.  grid = (ceil(N / (256*2)), B): blockIdx.y is the
 // image, so the (N,4) broadcast operand is indexed without a modulo; each thread keeps two
@@ -351,7 +403,10 @@ extern "C" int tfrpn_iou_map(const float* boxes, int boxes_batched, const float*
     const float4* b4 = reinterpret_cast<const float4*>(boxes);
     const float4* g4 = reinterpret_cast<const float4*>(gt_boxes);
     const long long bstride = boxes_batched ? (long long)N : 0LL;
-    if (cols) iou_map_kernel<true><<<grid, IOU_THREADS, smem, as_stream(s)>>>(b4, bstride, g4, N, G, out);
+    static const bool no_pairs = getenv("TFRPN_IOU_NO_PAIRS") != nullptr;   // A/B switch
+    if (!no_pairs && (G & 1) == 0 && G <= 2 * IOU_THREADS && (reinterpret_cast<uintptr_t>(out) & 7u) == 0)
+        iou_map_pairs_kernel<<<grid, IOU_THREADS, 0, as_stream(s)>>>(b4, bstride, g4, N, G, out);
+    else if (cols) iou_map_kernel<true><<<grid, IOU_THREADS, smem, as_stream(s)>>>(b4, bstride, g4, N, G, out);
     else iou_map_kernel<false><<<grid, IOU_THREADS, smem, as_stream(s)>>>(b4, bstride, g4, N, G, out);
     TFRPN_AFTER_LAUNCH("iou_map_kernel");
     return 0;
