@@ -65,7 +65,10 @@ def rand_boxes(rng, *shape):
 
 
 @pytest.mark.parametrize("B,N,G,batched", [(3, 257, 7, True), (3, 257, 7, False), (1, 1, 1, False), (2, 128, 50, True),
-                                           (2, 8649, 50, False), (2, 1000, 300, False), (5, 129, 3, True)])
+                                           (2, 8649, 50, False), (2, 1000, 300, False), (5, 129, 3, True),
+                                           # G % 4 == 0 / G % 2 == 0: 4 / 2 GT columns per thread (16- / 8-byte stores)
+                                           (2, 300, 200, True), (2, 513, 52, False), (3, 100, 6, True),
+                                           (1, 40, 1024, False), (1, 33, 600, False), (1, 20, 1026, False)])
 def test_iou_map_bit_exact(T, B, N, G, batched):
     rng = np.random.default_rng(B * 1000 + N + G)
     boxes = rand_boxes(rng, B, N) if batched else rand_boxes(rng, N)
@@ -909,3 +912,8 @@ def test_iou_map_nice_and_fallback_paths_agree_with_oracle(T):
     boxes = rand_boxes(rng, 4, 600)
     boxes[0, 5] = [0.2, 0.2, 0.2, 0.2]           # zero-area box in the tile: generic path, NaN-free here
     assert bits_equal(T.np(T.bbox.generate_iou_map(T.cu(boxes), T.cu(gtb))), O.generate_iou_map(boxes, gtb))
+    gt52, _ = synthetic.gt_batch(rng, 4, 52)     # four columns per thread, nice and not nice
+    assert bits_equal(T.np(T.bbox.generate_iou_map(T.cu(anchors), T.cu(gt52))), O.generate_iou_map(anchors, gt52))
+    gt52[3, 1] = [0.5, 0.5, 0.2, 0.2]
+    gt52[0, 2] = [1e-7, 0.1, 0.3, 0.4]
+    assert bits_equal(T.np(T.bbox.generate_iou_map(T.cu(anchors), T.cu(gt52))), O.generate_iou_map(anchors, gt52))

@@ -158,11 +158,13 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_map_kernel(const float4* __re
     }
 }
 
-// Even G (<= 256): a thread owns TWO adjacent GT columns and walks the rows, so one staged box serves two map
-// entries (one LDS.128 + one LDS per pair instead of per entry), both quotients come out of one packed
-// division, and the pair leaves as one 8-byte streaming store (row starts are 8-byte aligned when G is even):
-// half the load / store instructions of the one-column kernel.  IoU is symmetric in its two boxes down to the
-// bits (fmax / fmin / fadd commute), so iou_nice2 is called with the roles of box and GT swapped.
+// G a multiple of W = 2 or 4 (G <= W * 256): a thread owns W adjacent GT columns and walks the rows, so one
+// staged box serves W map entries (one LDS.128 + one LDS per W entries instead of per entry), the quotients come
+// out of packed divisions two at a time, and the W entries leave as one 8- or 16-byte streaming store (row
+// starts are 4W-byte aligned when W divides G): 1/W of the load / store instructions of the one-column
+// kernel.  IoU is symmetric in its two boxes down to the bits (fmax / fmin / fadd commute), so iou_nice2 is
+// called with the roles of box and GT swapped.
+template <int W>
 __global__ void __launch_bounds__(IOU_THREADS) iou_map_pairs_kernel(const float4* __restrict__ boxes,
                                                                     long long box_batch_stride,
                                                                     const float4* __restrict__ gt, int N, int G,
@@ -180,33 +182,40 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_map_pairs_kernel(const float4
         sbarea[i] = box_area(v);
         nice = nice && nice_box(v);
     }
-    const int H = G >> 1;                              // column pairs per row
+    const int H = G / W;                               // column groups per row
     const int R = IOU_THREADS / H;                     // rows per iteration
     const int r = threadIdx.x / H, h = threadIdx.x - r * H;
     const bool active = r < R;
-    const float4* gb = gt + (long long)b * G;
-    const float4 g0 = ldg_f4(gb + 2 * h), g1 = ldg_f4(gb + 2 * h + 1);
-    const float ga0 = box_area(g0), ga1 = box_area(g1);
-    nice = nice && nice_coords(g0) && g0.z >= g0.x && g0.w >= g0.y && nice_coords(g1) && g1.z >= g1.x && g1.w >= g1.y;
+    const float4* gb = gt + (long long)b * G + (active ? W * h : 0);
+    float4 g[W];
+    float ga[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        g[q] = ldg_f4(gb + q);
+        ga[q] = box_area(g[q]);
+        nice = nice && nice_coords(g[q]) && g[q].z >= g[q].x && g[q].w >= g[q].y;
+    }
     const bool all_nice = __syncthreads_and(nice) != 0;   // also publishes sbox / sbarea
     if (!active) return;
-    float2* o2 = reinterpret_cast<float2*>(out + ((long long)b * N + n0) * G);
-    asm("" : "+l"(o2));                                // keep the base in one register pair (IMAD.WIDE addressing)
-    unsigned e = threadIdx.x;                          // == r*H + h, in float2 units
+    float* o = out + ((long long)b * N + n0) * G;
+    asm("" : "+l"(o));                                 // keep the base in one register pair (IMAD.WIDE addressing)
+    unsigned e = threadIdx.x;                          // == r*H + h, in units of W floats
     const unsigned step = (unsigned)(R * H);
-    if (all_nice) {
-        const f32x2 ga2 = pack2(ga0, ga1);
 #pragma unroll 2
-        for (int n = r; n < tn; n += R, e += step) {
-            const float ba = sbarea[n];
-            float v0, v1;
-            iou_nice2(g0, g1, ga2, sbox[n], pack2(ba, ba), v0, v1);
-            stg_f2_stream(o2 + e, v0, v1);
+    for (int n = r; n < tn; n += R, e += step) {
+        const float4 bxn = sbox[n];
+        const float ba = sbarea[n];
+        float v[W];
+        if (all_nice) {
+            const f32x2 ba2 = pack2(ba, ba);
+#pragma unroll
+            for (int q = 0; q < W; q += 2) iou_nice2(g[q], g[q + 1], pack2(ga[q], ga[q + 1]), bxn, ba2, v[q], v[q + 1]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < W; ++q) v[q] = iou_ref(bxn, ba, g[q], ga[q]);
         }
-    } else {
-#pragma unroll 2
-        for (int n = r; n < tn; n += R, e += step)
-            stg_f2_stream(o2 + e, iou_ref(sbox[n], sbarea[n], g0, ga0), iou_ref(sbox[n], sbarea[n], g1, ga1));
+        if (W == 4) stg_f4_stream(reinterpret_cast<float4*>(o) + e, make_float4(v[0], v[1], v[2], v[3]));
+        else stg_f2_stream(reinterpret_cast<float2*>(o) + e, v[0], v[1]);
     }
 }
 
@@ -403,9 +412,12 @@ extern "C" int tfrpn_iou_map(const float* boxes, int boxes_batched, const float*
     const float4* b4 = reinterpret_cast<const float4*>(boxes);
     const float4* g4 = reinterpret_cast<const float4*>(gt_boxes);
     const long long bstride = boxes_batched ? (long long)N : 0LL;
-    static const bool no_pairs = getenv("TFRPN_IOU_NO_PAIRS") != nullptr;   // A/B switch
-    if (!no_pairs && (G & 1) == 0 && G <= 2 * IOU_THREADS && (reinterpret_cast<uintptr_t>(out) & 7u) == 0)
-        iou_map_pairs_kernel<<<grid, IOU_THREADS, 0, as_stream(s)>>>(b4, bstride, g4, N, G, out);
+    static const int max_w = getenv("TFRPN_IOU_W") ? atoi(getenv("TFRPN_IOU_W")) : 4;   // A/B switch: 1, 2 or 4
+    const uintptr_t oa = reinterpret_cast<uintptr_t>(out);
+    if (max_w >= 4 && (G & 3) == 0 && G <= 4 * IOU_THREADS && (oa & 15u) == 0)
+        iou_map_pairs_kernel<4><<<grid, IOU_THREADS, 0, as_stream(s)>>>(b4, bstride, g4, N, G, out);
+    else if (max_w >= 2 && (G & 1) == 0 && G <= 2 * IOU_THREADS && (oa & 7u) == 0)
+        iou_map_pairs_kernel<2><<<grid, IOU_THREADS, 0, as_stream(s)>>>(b4, bstride, g4, N, G, out);
     else if (cols) iou_map_kernel<true><<<grid, IOU_THREADS, smem, as_stream(s)>>>(b4, bstride, g4, N, G, out);
     else iou_map_kernel<false><<<grid, IOU_THREADS, smem, as_stream(s)>>>(b4, bstride, g4, N, G, out);
     TFRPN_AFTER_LAUNCH("iou_map_kernel");
