@@ -201,21 +201,31 @@ __global__ void __launch_bounds__(IOU_THREADS) iou_map_pairs_kernel(const float4
     asm("" : "+l"(o));                                 // keep the base in one register pair (IMAD.WIDE addressing)
     unsigned e = threadIdx.x;                          // == r*H + h, in units of W floats
     const unsigned step = (unsigned)(R * H);
+    auto store = [&](unsigned at, const float (&v)[W]) {
+        if constexpr (W == 4) stg_f4_stream(reinterpret_cast<float4*>(o) + at, make_float4(v[0], v[1], v[2], v[3]));
+        else stg_f2_stream(reinterpret_cast<float2*>(o) + at, v[0], v[1]);
+    };
+    if (all_nice) {   // separate loops: the choice is uniform, keep it out of the loop body
 #pragma unroll 2
-    for (int n = r; n < tn; n += R, e += step) {
-        const float4 bxn = sbox[n];
-        const float ba = sbarea[n];
-        float v[W];
-        if (all_nice) {
+        for (int n = r; n < tn; n += R, e += step) {
+            const float4 bxn = sbox[n];
+            const float ba = sbarea[n];
             const f32x2 ba2 = pack2(ba, ba);
+            float v[W];
 #pragma unroll
             for (int q = 0; q < W; q += 2) iou_nice2(g[q], g[q + 1], pack2(ga[q], ga[q + 1]), bxn, ba2, v[q], v[q + 1]);
-        } else {
+            store(e, v);
+        }
+    } else {
+#pragma unroll 1
+        for (int n = r; n < tn; n += R, e += step) {
+            const float4 bxn = sbox[n];
+            const float ba = sbarea[n];
+            float v[W];
 #pragma unroll
             for (int q = 0; q < W; ++q) v[q] = iou_ref(bxn, ba, g[q], ga[q]);
+            store(e, v);
         }
-        if (W == 4) stg_f4_stream(reinterpret_cast<float4*>(o) + e, make_float4(v[0], v[1], v[2], v[3]));
-        else stg_f2_stream(reinterpret_cast<float2*>(o) + e, v[0], v[1]);
     }
 }
 
