@@ -108,3 +108,29 @@ def test_expand_targets_host_matches_numpy_scatter():
         assert rc == 0 and np.array_equal(deltas, want), step
         prev, prev_tp = idx, TP
     assert lib.tfrpn_expand_targets_host(None, None, 1, 1, 1, None, 0, None) == -1
+
+
+def test_ctypes_structs_match_header_layout(tmp_path):
+    """Every struct that crosses the C ABI: size and field offsets of the ctypes mirror (tfrpn/_lib.py) equal
+    what a C compiler makes of include/tfrpn.h (the header is plain C: gcc compiles it without CUDA)."""
+    from tfrpn import _lib
+    pairs = {"tfrpn_anchor_cfg": _lib.AnchorCfg, "tfrpn_target_cfg": _lib.TargetCfg,
+             "tfrpn_target_debug": _lib.TargetDebug, "tfrpn_nms_cfg": _lib.NmsCfg,
+             "tfrpn_proposal_cfg": _lib.ProposalCfg, "tfrpn_loss_out": _lib.LossOut,
+             "tfrpn_step_buffers": _lib.StepBuffers}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tfrpn.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out.splitlines()}
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
