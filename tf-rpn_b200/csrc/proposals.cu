@@ -74,6 +74,7 @@ struct PropShared {
     unsigned int digit, remaining, bin_count;
     unsigned int count;
     int nk;
+    int nalive;
 };
 
 // score -> sortable key; entries at or below the score threshold get key 0 (below every real key)
@@ -363,18 +364,31 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 }
             }
             __syncthreads();
-            {   // intra-round predecessor masks: bit j of row i set iff j < i, both alive, j suppresses i.
+            if (warp == 0) {   // compact the candidates that survived the kept list (order preserved) into slot[]
+                int before = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = q * 32 + lane;
+                    const bool a = c < C && alive[c] != 0u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, a);
+                    if (a) slot[before + __popc(bal & ((1u << lane) - 1u))] = c;
+                    before += __popc(bal);
+                }
+                if (lane == 0) sh.nalive = before;
+            }
+            __syncthreads();
+            {   // intra-round predecessor masks over the A survivors: bit j of row i set iff j < i and j suppresses i.
                 // The triangle is folded so that every 16-thread team gets the same number of pairs:
-                // team r takes row iA = r + 1 (iA pairs) and row iB = C - 1 - r (iB pairs).
+                // team r takes row iA = r + 1 (iA pairs) and row iB = A - 1 - r (iB pairs) of the compact order.
+                const int A = sh.nalive;
                 const int r = tid >> 4, sub = tid & 15;
-                const int iA = r + 1, iB = C - 1 - r;
+                const int iA = r + 1, iB = A - 1 - r;
                 const int len = (iA < iB) ? iA + iB : (iA == iB ? iA : 0);
                 for (int e = sub; e < len; e += 16) {
-                    const int i = e < iA ? iA : iB;
-                    const int j = e < iA ? e : e - iA;
-                    if (alive[i] && alive[j] &&
-                        (thr.fast ? nms_suppresses_fast(cbox[j], carea[j], cbox[i], carea[i], thr)
-                                  : nms_suppresses(cbox[j], carea[j], cbox[i], carea[i], thr)))
+                    const int i = slot[e < iA ? iA : iB];
+                    const int j = slot[e < iA ? e : e - iA];
+                    if (thr.fast ? nms_suppresses_fast(cbox[j], carea[j], cbox[i], carea[i], thr)
+                                 : nms_suppresses(cbox[j], carea[j], cbox[i], carea[i], thr))
                         atomicOr(&mask32[i * 4 + (j >> 5)], 1u << (j & 31));
                 }
             }
