@@ -1,8 +1,10 @@
 // api.cu -- handle, error reporting, workspace, and the host-buffer entry points of libtfrpn_cuda.so.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -30,6 +32,35 @@ size_t targets_workspace_bytes(int B, int N, int G);  // targets.cu
 size_t prefilter_workspace_bytes(int B, int N, int k);  // proposals.cu (0 when the prefilter does not apply)
 
 int sm_count_of(tfrpn_handle h) { return h ? h->sm_count : 148; }
+
+int device_of_pointer(const void* p) {
+    if (!p) return -1;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) return -1;
+    return attr.device;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: set it once for every
+// device a call touches (not once per thread), with that device current.
+int ensure_kernel_attributes(int device) {
+    constexpr int MAX_DEV = 64;
+    static bool done[MAX_DEV] = {};
+    static std::mutex mu;
+    if (device < 0 || device >= MAX_DEV) return fail(TFRPN_ERR_BAD_ARG, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[device]) return 0;
+    if (int rc = set_attributes_targets()) return rc;
+    if (int rc = set_attributes_proposals()) return rc;
+    if (int rc = set_attributes_boxmath()) return rc;
+    done[device] = true;
+    return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 int grow_buffer(char** buf, size_t* have, size_t want, cudaStream_t s, bool pinned) {
     if (want <= *have) return 0;
@@ -89,12 +120,14 @@ extern "C" uint64_t tfrpn_launch_count(void) { return g_launches; }
 
 extern "C" int tfrpn_profile_enable(tfrpn_handle h, int on) {
     if (!h) return fail(TFRPN_ERR_BAD_ARG, "profile_enable: null handle");
+    TFRPN_ENTER(h);
     h->prof_on = on != 0;
     return 0;
 }
 
 extern "C" int tfrpn_profile_read(tfrpn_handle h, int kernel_id, double* total_ms, int* launches) {
     if (!h || !total_ms || !launches) return fail(TFRPN_ERR_BAD_ARG, "profile_read: null pointer");
+    TFRPN_ENTER(h);
     TFRPN_CHECK_CUDA(cudaDeviceSynchronize());
     double ms = 0;
     int n = 0;
@@ -133,9 +166,18 @@ extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
                     e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
     if (device < 0) TFRPN_CHECK_CUDA(cudaGetDevice(&device));
     if (device >= count) return fail(TFRPN_ERR_BAD_ARG, "create: device %d of %d", device, count);
-    TFRPN_CHECK_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);   // the caller's current device is restored on return
+    if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
+    if (int rc = ensure_kernel_attributes(device)) return rc;
     tfrpn_ctx* h = new tfrpn_ctx();
     h->device = device;
+    // A/B switches: read here, once per handle, never on the launch path
+    h->opts.k2_apt = env_int("TFRPN_K2_APT", 0);
+    h->opts.k2_scalar = getenv("TFRPN_K2_SCALAR") != nullptr;
+    h->opts.pipe_dense = getenv("TFRPN_PIPE_DENSE") != nullptr;
+    h->opts.pipe_chunks = env_int("TFRPN_PIPE_CHUNKS", 0);
+    h->opts.prop_cluster = env_int("TFRPN_PROP_CLUSTER", -1);
+    h->opts.pipe_dense_in = getenv("TFRPN_PIPE_DENSE_IN") != nullptr;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     // device counter of the loss reduction (losses.cu): zero between calls, the kernel resets it
     if (cudaMalloc(&h->ticket, 256) != cudaSuccess || cudaMemset(h->ticket, 0, 256) != cudaSuccess) {
@@ -149,6 +191,7 @@ extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
 
 extern "C" int tfrpn_destroy(tfrpn_handle h) {
     if (!h) return 0;
+    DeviceGuard guard(h->device);
     if (h->ws) cudaFree(h->ws);
     if (h->ws_prop) cudaFree(h->ws_prop);
     if (h->dev) cudaFree(h->dev);
@@ -170,6 +213,7 @@ extern "C" size_t tfrpn_workspace_bytes(int B, int N, int G, int k) {
 
 extern "C" int tfrpn_reserve(tfrpn_handle h, int B, int N, int G, int k) {
     if (!h) return fail(TFRPN_ERR_BAD_ARG, "reserve: null handle");
+    TFRPN_ENTER(h);
     char* ws;
     if (B <= 0 || N <= 0) return 0;
     if (int rc = ensure_workspace(h, targets_workspace_bytes(B, N, G > 0 ? G : 1), nullptr, &ws)) return rc;
@@ -290,6 +334,7 @@ extern "C" int tfrpn_rpn_targets_host(tfrpn_handle h, const float* anchors_dev, 
                                       const int32_t* gt_labels_host, int B, int N, int G, const tfrpn_target_cfg* cfg,
                                       float* deltas_host, float* labels_host, tfrpn_stream s) {
     if (!h) return fail(TFRPN_ERR_BAD_ARG, "rpn_targets_host: null handle");
+    TFRPN_ENTER(h);
     HostJob job;
     if (int rc = targets_host_enqueue(h, anchors_dev, gt_boxes_host, gt_labels_host, B, N, G, cfg, deltas_host,
                                       labels_host, as_stream(s), job)) return rc;
@@ -303,6 +348,7 @@ extern "C" int tfrpn_proposals_host(tfrpn_handle h, const float* rpn_reg_host, c
                                     float* out_boxes_host, float* out_scores_host, int32_t* valid_host,
                                     int32_t* keep_idx_host_or_null, tfrpn_stream s) {
     if (!h) return fail(TFRPN_ERR_BAD_ARG, "proposals_host: null handle");
+    TFRPN_ENTER(h);
     HostJob job;
     if (int rc = proposals_host_enqueue(h, rpn_reg_host, rpn_cls_host, anchors_dev, B, N, cfg, out_boxes_host,
                                         out_scores_host, valid_host, keep_idx_host_or_null, as_stream(s), job)) return rc;

@@ -364,6 +364,11 @@ __global__ void __launch_bounds__(256) selftest_division_kernel(unsigned long lo
     if (bad) atomicAdd(mismatches, bad);
 }
 
+int set_attributes_boxmath() {
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(iou_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return 0;
+}
+
 static int ew_grid(long long total, int per_thread) {
     long long blocks = (total + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
     if (blocks < 1) blocks = 1;
@@ -388,6 +393,7 @@ extern "C" int tfrpn_anchors(const tfrpn_anchor_cfg* cfg, float* out, tfrpn_stre
     if (int rc = check_anchor_cfg(cfg)) return rc;
     if (!out) return fail(TFRPN_ERR_BAD_ARG, "out is null");
     if (!aligned16(out)) return fail(TFRPN_ERR_MISALIGNED, "anchors output must be 16-byte aligned");
+    TFRPN_ENTER_PTR(out, "anchors: out");
     BaseAnchors base;
     float tmp[TFRPN_MAX_BASE_ANCHORS * 4];
     base_anchors_host(cfg, tmp);
@@ -413,11 +419,7 @@ extern "C" int tfrpn_iou_map(const float* boxes, int boxes_batched, const float*
     const bool cols = G <= 128;
     size_t smem = (size_t)(IOU_TILE_N + (cols ? 0 : G)) * (sizeof(float4) + sizeof(float));
     if (smem > 200 * 1024) return fail(TFRPN_ERR_UNSUPPORTED, "iou_map: G=%d too large for shared memory", G);
-    static thread_local bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        TFRPN_CHECK_CUDA(cudaFuncSetAttribute(iou_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    TFRPN_ENTER_PTR(out, "iou_map: out");
     dim3 grid((N + IOU_TILE_N - 1) / IOU_TILE_N, B);
     const float4* b4 = reinterpret_cast<const float4*>(boxes);
     const float4* g4 = reinterpret_cast<const float4*>(gt_boxes);
@@ -443,6 +445,7 @@ extern "C" int tfrpn_encode_deltas(const float* boxes, int boxes_batched, const 
     if (!aligned16(boxes) || !aligned16(gt_boxes) || !aligned16(out))
         return fail(TFRPN_ERR_MISALIGNED, "encode: pointers must be 16-byte aligned");
     if (B > 65535) return fail(TFRPN_ERR_UNSUPPORTED, "encode: B > 65535");
+    TFRPN_ENTER_PTR(out, "encode: out");
     encode_kernel<<<ew_grid2(B, N), EW_THREADS, 0, as_stream(s)>>>(
         reinterpret_cast<const float4*>(boxes), boxes_batched, reinterpret_cast<const float4*>(gt_boxes), N,
         reinterpret_cast<float4*>(out));
@@ -467,9 +470,9 @@ extern "C" int tfrpn_decode(const float* anchors, int anchors_batched, const flo
     const float4* d4 = reinterpret_cast<const float4*>(deltas);
     float4* o4 = reinterpret_cast<float4*>(out);
     if (B > 65535) return fail(TFRPN_ERR_UNSUPPORTED, "decode: B > 65535");
+    TFRPN_ENTER_PTR(out, "decode: out");
     cudaStream_t st = as_stream(s);
-    static int pt = 0;
-    if (pt == 0) { const char* e = getenv("TFRPN_DECODE_PT"); pt = e ? atoi(e) : 2; if (pt != 1 && pt != 2 && pt != 4) pt = 2; }
+    static const int pt = [] { const char* e = getenv("TFRPN_DECODE_PT"); const int v = e ? atoi(e) : 2; return (v == 1 || v == 4) ? v : 2; }();
 #define TFRPN_DECODE_LAUNCH(PT)                                                                                      \
     do {                                                                                                             \
         dim3 grid((N + EW_THREADS * PT - 1) / (EW_THREADS * PT), B);                                                 \
@@ -490,6 +493,7 @@ extern "C" int tfrpn_scale_boxes(const float* boxes, int64_t n_boxes, float heig
     if (n_boxes < 0) return fail(TFRPN_ERR_BAD_ARG, "scale_boxes: negative count");
     if (n_boxes == 0) return 0;
     if (!aligned16(boxes) || !aligned16(out)) return fail(TFRPN_ERR_MISALIGNED, "scale_boxes: 16-byte alignment");
+    TFRPN_ENTER_PTR(out, "scale_boxes: out");
     scale_boxes_kernel<<<ew_grid(n_boxes, 1), EW_THREADS, 0, as_stream(s)>>>(
         reinterpret_cast<const float4*>(boxes), n_boxes, height, width, denormalize, reinterpret_cast<float4*>(out));
     TFRPN_AFTER_LAUNCH("scale_boxes_kernel");
@@ -505,6 +509,7 @@ extern "C" int tfrpn_pad_gt(const float* flat_boxes, const int32_t* flat_labels,
     if (!flat_boxes || !flat_labels) return fail(TFRPN_ERR_BAD_ARG, "pad_gt: null pointer");
     if ((long long)B * G > (1LL << 30)) return fail(TFRPN_ERR_UNSUPPORTED, "pad_gt: B*G too large");
     if (!aligned16(flat_boxes) || !aligned16(out_boxes)) return fail(TFRPN_ERR_MISALIGNED, "pad_gt: boxes must be 16-byte aligned");
+    TFRPN_ENTER_PTR(out_boxes, "pad_gt: out_boxes");
     const int blocks = (B * G + EW_THREADS - 1) / EW_THREADS;
     pad_gt_kernel<<<blocks, EW_THREADS, 0, as_stream(s)>>>(reinterpret_cast<const float4*>(flat_boxes), flat_labels, offsets,
                                                            flip_or_null, B, G, label_add,
@@ -515,6 +520,7 @@ extern "C" int tfrpn_pad_gt(const float* flat_boxes, const int32_t* flat_labels,
 
 extern "C" int tfrpn_selftest_division(uint64_t n_pairs, uint64_t seed, uint64_t* mismatches_dev, tfrpn_stream s) {
     if (!mismatches_dev) return fail(TFRPN_ERR_BAD_ARG, "selftest_division: null pointer");
+    TFRPN_ENTER_PTR(mismatches_dev, "selftest_division: mismatches_dev");
     TFRPN_CHECK_CUDA(cudaMemsetAsync(mismatches_dev, 0, sizeof(uint64_t), as_stream(s)));
     if (n_pairs == 0) return 0;
     selftest_division_kernel<<<148 * 8, 256, 0, as_stream(s)>>>(n_pairs, seed, reinterpret_cast<unsigned long long*>(mismatches_dev));

@@ -290,6 +290,8 @@ extern "C" int tfrpn_rpn_losses(tfrpn_handle h, const float* true_deltas, const 
     if (!(huber_delta > 0.0f)) return fail(TFRPN_ERR_BAD_ARG, "rpn_losses: huber_delta must be > 0");
     if (true_deltas && (!aligned16(true_deltas) || !aligned16(pred_deltas) || (grad_deltas_or_null && !aligned16(grad_deltas_or_null))))
         return fail(TFRPN_ERR_MISALIGNED, "rpn_losses: delta tensors must be 16-byte aligned");
+    TFRPN_ENTER(h);
+    TFRPN_CHECK_ON_DEVICE(h, out, "rpn_losses: out");
     cudaStream_t st = as_stream(s);
     const long long total = (long long)B * N;
     if (total > (1LL << 38)) return fail(TFRPN_ERR_UNSUPPORTED, "rpn_losses: tensor too large");

@@ -81,7 +81,7 @@ namespace tfrpn {
 
 void pipe_destroy(tfrpn_pipe* p) {
     if (!p) return;
-    cudaSetDevice(p->h->device);
+    DeviceGuard guard(p->h->device);
     for (cudaStream_t s : {p->s_in, p->s_tgt, p->s_prop, p->s_out})
         if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     if (p->ev_after) cudaEventDestroy(p->ev_after);
@@ -102,7 +102,7 @@ void pipe_destroy(tfrpn_pipe* p) {
 static int pipe_create(tfrpn_handle h, int depth, tfrpn_pipe** out) {
     if (!h || !out) return fail(TFRPN_ERR_BAD_ARG, "pipeline_create: null pointer");
     if (depth < 1 || depth > MAX_DEPTH) return fail(TFRPN_ERR_BAD_ARG, "pipeline_create: depth must be 1..%d", MAX_DEPTH);
-    TFRPN_CHECK_CUDA(cudaSetDevice(h->device));
+    TFRPN_ENTER(h);
     tfrpn_pipe* p = new tfrpn_pipe();
     p->h = h;
     p->depth = depth;
@@ -207,7 +207,8 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     if (do_p && (!a.rpn_cls || !a.pcfg || !a.out_boxes || !a.out_scores || !a.valid || a.pcfg->post_nms_topn <= 0))
         return fail(TFRPN_ERR_BAD_ARG, "pipeline_submit: proposal half needs rpn_cls, cfg, out_boxes, out_scores, valid");
     tfrpn_handle h = p->h;
-    TFRPN_CHECK_CUDA(cudaSetDevice(h->device));
+    TFRPN_ENTER(h);
+    TFRPN_CHECK_ON_DEVICE(h, a.anchors_dev, "pipeline_submit: anchors_dev");
     const int B = a.B, N = a.N, G = a.G > 0 ? a.G : 1;
     const int P = acquired ? p->acq_P : (do_p ? a.pcfg->post_nms_topn : 1);
     Slot& s = p->slots[p->next_ticket % p->depth];
@@ -245,13 +246,15 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     // Acquired slots return bbox_deltas in compact form (2.8 MB of results instead of 11.5 MB per C2 step: the
     // deltas are exactly zero outside the <= total_pos sampled positives, utils/train_utils.py:137);
     // slot_finish expands them into the slot's dense host array.
-    static const bool force_dense = getenv("TFRPN_PIPE_DENSE") != nullptr;
-    const bool compact = acquired && do_t && !force_dense && a.tcfg->total_pos <= COMPACT_MAX_POS;
-    if (do_t && !compact) s.dense_clean = false;   // the dense arrays are about to be overwritten wholesale
+    const bool compact = acquired && do_t && !h->opts.pipe_dense && a.tcfg->total_pos <= COMPACT_MAX_POS;
+    // The incremental expansion of slot_finish relies on the slot's dense deltas region still holding zeros plus
+    // the previous step's rows.  Any step that is not a compact step of the SAME layout may write into that
+    // region (dense results, or the inputs / results of another (B,N,G,P) layout): forget the invariant.
+    if (!(compact && s.pB == B && s.pN == N && s.p_off_d == L.d)) s.dense_clean = false;
     // A synchronous step (depth 1) is chunked over images so that copies overlap its own kernels; with
     // several steps in flight the overlap comes from the neighbouring steps and fewer, larger copies win.
     int chunks = (p->depth == 1 && !acquired) ? (B >= 32 ? 4 : (B >= 8 ? 2 : 1)) : 1;
-    if (const char* e = getenv("TFRPN_PIPE_CHUNKS")) chunks = atoi(e);
+    if (h->opts.pipe_chunks > 0) chunks = h->opts.pipe_chunks;
     chunks = chunks < 1 ? 1 : (chunks > MAX_CHUNKS ? MAX_CHUNKS : chunks);
     if (acquired) {
         // one copy for all inputs of the halves that run
@@ -309,7 +312,7 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         TFRPN_CHECK_CUDA(cudaStreamWaitEvent(p->s_out, s.ev_prop, 0));
         if (!acquired) {
             // the four small proposal results come back in ONE D2H copy through pinned staging
-            TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin + L.ob, d + L.ob, L.total - L.ob, cudaMemcpyDeviceToHost, p->s_out));
+            TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin + L.ob, d + L.ob, L.dense_end - L.ob, cudaMemcpyDeviceToHost, p->s_out));
             s.defer(a.out_boxes, pin + L.ob, (size_t)B * P * 16);
             s.defer(a.out_scores, pin + L.os, (size_t)B * P * 4);
             s.defer(a.valid, pin + L.v, (size_t)B * 4);
@@ -371,7 +374,7 @@ extern "C" int tfrpn_pipeline_submit(tfrpn_pipeline p, const float* anchors_dev,
 extern "C" int tfrpn_pipeline_acquire(tfrpn_pipeline p, int B, int N, int G, int post_nms_topn, tfrpn_step_buffers* out) {
     if (!p || !out) return fail(TFRPN_ERR_BAD_ARG, "pipeline_acquire: null pointer");
     if (B <= 0 || N <= 0 || G <= 0 || post_nms_topn <= 0) return fail(TFRPN_ERR_BAD_ARG, "pipeline_acquire: bad shape");
-    TFRPN_CHECK_CUDA(cudaSetDevice(p->h->device));
+    TFRPN_ENTER(p->h);
     Slot& s = p->slots[p->next_ticket % p->depth];
     if (int rc = slot_finish(p, s)) return rc;
     const Layout L = make_layout(B, N, G, post_nms_topn);
@@ -429,11 +432,13 @@ extern "C" int tfrpn_pipeline_last_copy_bytes(tfrpn_pipeline p, int64_t* h2d_byt
 
 extern "C" int tfrpn_pipeline_wait(tfrpn_pipeline p, int64_t ticket) {
     if (!p) return fail(TFRPN_ERR_BAD_ARG, "pipeline_wait: null pipeline");
+    TFRPN_ENTER(p->h);
     return pipe_wait(p, ticket);
 }
 
 extern "C" int tfrpn_pipeline_drain(tfrpn_pipeline p) {
     if (!p) return fail(TFRPN_ERR_BAD_ARG, "pipeline_drain: null pipeline");
+    TFRPN_ENTER(p->h);
     for (int i = 0; i < p->depth; ++i) if (int rc = slot_finish(p, p->slots[i])) return rc;
     return 0;
 }
@@ -450,6 +455,7 @@ extern "C" int tfrpn_rpn_step_host(tfrpn_handle h, const float* anchors_dev, con
         !pcfg || !out_boxes_host || !out_scores_host || !valid_host)
         return fail(TFRPN_ERR_BAD_ARG, "rpn_step_host: null pointer");
     if (B <= 0 || N <= 0 || G <= 0 || pcfg->post_nms_topn <= 0) return fail(TFRPN_ERR_BAD_ARG, "rpn_step_host: bad shape");
+    TFRPN_ENTER(h);
     if (!h->step_pipe) if (int rc = pipe_create(h, 1, &h->step_pipe)) return rc;
     StepArgs a = {anchors_dev, gt_boxes_host, gt_labels_host, B, N, G, tcfg, deltas_host, labels_host,
                   rpn_reg_host, rpn_cls_host, pcfg, out_boxes_host, out_scores_host, valid_host, keep_idx_host_or_null};

@@ -465,6 +465,11 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     if (tid == 0) p.valid[b] = nkept;
 }
 
+int set_attributes_proposals() {
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 4096)));
+    return 0;
+}
+
 static IouThreshold make_threshold(float thr) {
     IouThreshold t;
     t.thr = thr;
@@ -798,11 +803,6 @@ static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
     if (smem > PROP_SMEM_LIMIT)
         return fail(TFRPN_ERR_UNSUPPORTED, "NMS: %d output rows need %zu B of shared memory (> %zu)", p.max_out, smem,
                     PROP_SMEM_LIMIT);
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROP_SMEM_LIMIT));
-        attr_set = true;
-    }
     prof_begin(h, TFRPN_K_PROPOSAL, st);
     proposal_kernel<<<B, PR_THREADS, smem, st>>>(p);
     prof_end(h, st);
@@ -824,6 +824,9 @@ extern "C" int tfrpn_topk(tfrpn_handle h, const float* scores, int B, int N, int
     if (boxes_or_null && (!aligned16(boxes_or_null) || !aligned16(gathered_or_null)))
         return fail(TFRPN_ERR_MISALIGNED, "topk: boxes must be 16-byte aligned");
     if (B == 0 || k == 0) return 0;
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "topk: null handle");
+    TFRPN_ENTER(h);
+    TFRPN_CHECK_ON_DEVICE(h, scores, "topk: scores");
     PropParams p = {};
     p.mode = MODE_TOPK; p.N = N; p.k = k; p.scores = scores; p.use_sthr = 0;
     p.boxes = reinterpret_cast<const float4*>(boxes_or_null); p.box_stride = boxes_batched ? N : 0;
@@ -842,6 +845,9 @@ extern "C" int tfrpn_predict_topk(tfrpn_handle h, const float* rpn_reg, const fl
     if (!aligned16(rpn_reg) || !aligned16(anchors) || !aligned16(out_boxes))
         return fail(TFRPN_ERR_MISALIGNED, "predict_topk: rpn_reg / anchors / out_boxes must be 16-byte aligned");
     if (B == 0 || k == 0) return 0;
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "predict_topk: null handle");
+    TFRPN_ENTER(h);
+    TFRPN_CHECK_ON_DEVICE(h, rpn_reg, "predict_topk: rpn_reg");
     PropParams p = {};
     p.mode = MODE_TOPK; p.N = N; p.k = k; p.scores = rpn_cls; p.use_sthr = 0;
     p.reg = reinterpret_cast<const float4*>(rpn_reg); p.anchors = reinterpret_cast<const float4*>(anchors);
@@ -861,6 +867,9 @@ extern "C" int tfrpn_nms(tfrpn_handle h, const float* boxes, const float* scores
         return fail(TFRPN_ERR_BAD_ARG, "nms: max_output_size_per_class and max_total_size must be > 0");
     if (!aligned16(boxes) || !aligned16(out_boxes)) return fail(TFRPN_ERR_MISALIGNED, "nms: boxes must be 16-byte aligned");
     if (B == 0) return 0;
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "nms: null handle");
+    TFRPN_ENTER(h);
+    TFRPN_CHECK_ON_DEVICE(h, boxes, "nms: boxes");
     PropParams p = {};
     if (cfg->pre_nms_topn < 0) return fail(TFRPN_ERR_BAD_ARG, "nms: pre_nms_topn must be >= 0");
     p.mode = MODE_NMS; p.N = K; p.k = cfg->pre_nms_topn > 0 ? min(K, cfg->pre_nms_topn) : K; p.scores = scores;
@@ -885,6 +894,9 @@ extern "C" int tfrpn_proposals(tfrpn_handle h, const float* rpn_reg, const float
     if (!aligned16(rpn_reg) || !aligned16(anchors) || !aligned16(out_boxes))
         return fail(TFRPN_ERR_MISALIGNED, "proposals: rpn_reg / anchors / out_boxes must be 16-byte aligned");
     if (B == 0) return 0;
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "proposals: null handle");
+    TFRPN_ENTER(h);
+    TFRPN_CHECK_ON_DEVICE(h, rpn_reg, "proposals: rpn_reg");
     PropParams p = {};
     p.mode = MODE_PROPOSALS; p.N = N; p.k = min(cfg->pre_nms_topn, N); p.scores = rpn_cls; p.use_sthr = 0;
     p.reg = reinterpret_cast<const float4*>(rpn_reg); p.anchors = reinterpret_cast<const float4*>(anchors);

@@ -49,6 +49,7 @@ class StepBuffers(C.Structure):
 
 P = C.c_void_p
 I = C.c_int
+KERNEL_IDS = 5   # TFRPN_K_COUNT of include/tfrpn.h
 # name -> (restype, argtypes); must list every symbol include/tfrpn.h declares
 PROTOTYPES = {
     "tfrpn_version": (I, []),

@@ -39,14 +39,20 @@ def _is_tf(x):
     return type(x).__module__.split(".")[0] == "tensorflow"
 
 
-def to_device(x, dtype, origin, name="tensor"):
-    """-> contiguous torch CUDA tensor of `dtype` (float32 tensors are never cast silently)."""
+def ingest(x, origin, name="tensor"):
+    """-> a torch view of `x` wherever it lives (no copy for torch tensors and DLPack producers).
+
+    DLPack stream contract: ``torch.from_dlpack`` calls ``x.__dlpack__(stream=s)`` with ``s`` = torch's CURRENT
+    stream on the producer's device (1 for the legacy default stream), and the producer must make the tensor's
+    pending writes visible to work later enqueued on ``s`` -- the stream every kernel of this call is launched on
+    (``stream_ptr``).  So a producer that computes on its own stream (TensorFlow) is ordered before our kernels
+    by the protocol itself, not by an assumption about default streams."""
     if isinstance(x, torch.Tensor):
         t = x
         origin.note("torch" if t.is_cuda else "torch_cpu", t.device)
     elif isinstance(x, np.ndarray) or isinstance(x, (list, tuple, float, int)):
         a = np.asarray(x)
-        if a.dtype == np.float64 and dtype == torch.float32 and not isinstance(x, np.ndarray):
+        if a.dtype == np.float64 and not isinstance(x, np.ndarray):
             a = a.astype(np.float32)   # Python lists of floats, like TF's convert_to_tensor
         t = torch.from_numpy(np.ascontiguousarray(a))
         origin.note("numpy", None)
@@ -59,6 +65,12 @@ def to_device(x, dtype, origin, name="tensor"):
         origin.note("dlpack", t.device)
     else:
         raise TypeError("%s: unsupported tensor type %r" % (name, type(x)))
+    return t
+
+
+def to_device(x, dtype, origin, name="tensor"):
+    """-> contiguous torch CUDA tensor of `dtype` (float32 tensors are never cast silently)."""
+    t = ingest(x, origin, name)
     if dtype == torch.float32 and t.dtype != torch.float32:
         raise ValueError("%s must be float32, got %s" % (name, t.dtype))
     if dtype == torch.int32 and t.dtype in (torch.int64, torch.int16, torch.int8, torch.uint8):

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._tensor import default_device
+from ._tensor import Origin, default_device, to_device
 from .proposals import proposal_cfg
 from .utils import bbox_utils, train_utils
 
@@ -49,16 +49,31 @@ class HostPipeline:
         self.device = dev
         self.hp = hyper_params
         self.depth = int(depth)
+        self._pipe = self._h = None
         with torch.cuda.device(dev):
-            self.anchors = bbox_utils.generate_anchors(hyper_params) if anchors is None else anchors
+            if anchors is None:
+                anchors = bbox_utils.generate_anchors(hyper_params)
+            else:   # host arrays / CPU tensors are copied to this GPU; a tensor on another GPU is rejected
+                o = Origin()
+                o.note(None, dev)
+                anchors = to_device(anchors, torch.float32, o, "anchors")
             torch.cuda.synchronize()
+        if anchors.dim() != 2 or anchors.shape[1] != 4:
+            raise ValueError("anchors must be (total_anchors, 4), got %s" % (tuple(anchors.shape),))
+        self.anchors = anchors          # contiguous float32 CUDA tensor on self.device, kept alive here
         self.N = int(self.anchors.shape[0])
         self.pcfg = proposal_cfg(hyper_params, pre_nms_topn=pre_nms_topn)
         self.P = int(self.pcfg.post_nms_topn)
         self._lib = _lib.load()
-        self._h = _lib.handle(dev.index)
-        self._pipe = C.c_void_p()
-        _lib.check(self._lib.tfrpn_pipeline_create(self._h, self.depth, C.byref(self._pipe)))
+        # The pipeline's steps run on its own streams while the caller keeps using the drop-in functions
+        # (losses, calculate_rpn_actual_outputs, ...) on torch's stream with the thread's shared handle: the
+        # pipeline therefore owns a handle (= workspace) of its own.
+        h = C.c_void_p()
+        _lib.check(self._lib.tfrpn_create(C.byref(h), int(dev.index)))
+        self._h = h
+        pipe = C.c_void_p()
+        _lib.check(self._lib.tfrpn_pipeline_create(self._h, self.depth, C.byref(pipe)))
+        self._pipe = pipe
         self._views = {}
 
     def acquire(self, batch, max_gt):
@@ -105,8 +120,11 @@ class HostPipeline:
     def close(self):
         if self._pipe:
             self._lib.tfrpn_pipeline_destroy(self._pipe)
-            self._pipe = C.c_void_p()
+            self._pipe = None
             self._views.clear()
+        if self._h:
+            self._lib.tfrpn_destroy(self._h)
+            self._h = None
 
     def __del__(self):
         try:
