@@ -26,6 +26,9 @@ size_t targets_workspace_bytes(int B, int N, int G);  // targets.cu
 int launch_targets(tfrpn_handle h, const float* anchors, const float* gt_boxes, const int32_t* gt_labels, int B, int N,
                    int G, const tfrpn_target_cfg* cfg, float* deltas, float* labels, int32_t* pos_idx,
                    float* pos_deltas, const tfrpn_target_debug* dbg, tfrpn_stream s);
+int proposals_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B, int N,
+                      const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
+                      int32_t* keep_idx_or_null, unsigned long long* rows_fetched_or_null, cudaStream_t st);   // proposals.cu
 }
 
 namespace {
@@ -51,6 +54,8 @@ struct Slot {
     long long ticket = -1;          // ticket in flight in this slot (-1 = free)
     // compact results (acquired mode): bbox_deltas comes back as its <= total_pos non-zero rows per image and is
     // expanded into the slot's dense host array when the step is retired (the labels travel as they are)
+    bool pulled = false;            // the step in flight pulls rpn_reg rows from the pinned block (row count at off_pc)
+    size_t off_pc = 0;
     bool compact = false;           // the step in flight returns compact targets
     int cB = 0, cN = 0, cTP = 0;    // its shape
     size_t off_d = 0, off_ci = 0, off_cd = 0;
@@ -75,6 +80,7 @@ struct tfrpn_pipe {
     int acq_B = 0, acq_N = 0, acq_G = 0, acq_P = 0;   // shape of the slot handed out by the last acquire()
     bool acq_live = false;
     long long last_h2d = 0, last_d2h = 0;             // bytes copied by the last submitted step
+    long long last_pulled = 0;                        // bytes of rpn_reg rows pulled by the kernels of the last RETIRED step
 };
 
 namespace tfrpn {
@@ -130,6 +136,10 @@ static int slot_finish(tfrpn_pipe* p, Slot& s) {
     TFRPN_CHECK_CUDA(cudaEventSynchronize(s.ev_done));
     for (int i = 0; i < s.n_copies; ++i) memcpy(s.copies[i].dst, s.copies[i].src, s.copies[i].bytes);
     s.n_copies = 0;
+    if (s.pulled) {
+        p->last_pulled = 16LL * (long long)*reinterpret_cast<const unsigned long long*>(s.pin + s.off_pc);
+        s.pulled = false;
+    }
     if (s.compact) {   // expand into the dense (B,N,4) / (B,N) host arrays of this slot
         const bool reuse = s.dense_clean && s.pB == s.cB && s.pN == s.cN && s.p_off_d == s.off_d;
         const int32_t* idx = reinterpret_cast<const int32_t*>(s.pin + s.off_ci);
@@ -160,8 +170,8 @@ struct StepArgs {
 // is one H2D and one D2H copy -- on this link several copies per direction cost 30 % of the duplex
 // rate (tools/src/pcie_pattern.cu: 309 us vs 231 us per C2 step).
 struct Layout {
-    size_t gt, gl, reg, cls, in_end;            // inputs
-    size_t d, l, ob, os, v, k, dense_end;       // results
+    size_t gt, gl, cls, small_end, reg, in_end; // inputs: the small ones first, the head's regression output last
+    size_t d, l, ob, os, v, k, pc, dense_end;   // results (pc: rows of rpn_reg the proposal kernels pulled)
     size_t ci, cd, total;                       // compact bbox_deltas (row indices, rows)
 };
 static Layout make_layout(int B, int N, int G, int P) {
@@ -169,8 +179,9 @@ static Layout make_layout(int B, int N, int G, int P) {
     size_t o = 0;
     L.gt = o;  o += align256((size_t)B * G * 16);
     L.gl = o;  o += align256((size_t)B * G * 4);
-    L.reg = o; o += align256((size_t)B * N * 16);
     L.cls = o; o += align256((size_t)B * N * 4);
+    L.small_end = o;
+    L.reg = o; o += align256((size_t)B * N * 16);
     L.in_end = o;
     L.d = o;   o += align256((size_t)B * N * 16);
     L.l = o;   o += align256((size_t)B * N * 4);
@@ -178,6 +189,7 @@ static Layout make_layout(int B, int N, int G, int P) {
     L.os = o;  o += align256((size_t)B * P * 4);
     L.v = o;   o += align256((size_t)B * 4);
     L.k = o;   o += align256((size_t)B * P * 4);
+    L.pc = o;  o += 256;
     L.dense_end = o;
     L.ci = o;  o += align256((size_t)B * COMPACT_MAX_POS * 4);
     L.cd = o;  o += align256((size_t)B * COMPACT_MAX_POS * 16);
@@ -256,11 +268,16 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     int chunks = (p->depth == 1 && !acquired) ? (B >= 32 ? 4 : (B >= 8 ? 2 : 1)) : 1;
     if (h->opts.pipe_chunks > 0) chunks = h->opts.pipe_chunks;
     chunks = chunks < 1 ? 1 : (chunks > MAX_CHUNKS ? MAX_CHUNKS : chunks);
+    // Acquired slots: rpn_reg stays in the slot's page-locked host block and the proposal kernels pull the rows of
+    // the candidates they examine (<= ~1000 of N per image) over PCIe with their own loads -- 1 MB of 16-byte rows
+    // instead of an 8.9 MB copy at C2.  TFRPN_PIPE_DENSE_IN=1 copies the whole tensor as before (A/B switch).
+    const bool pull_reg = acquired && do_p && !h->opts.pipe_dense_in;
     if (acquired) {
-        // one copy for all inputs of the halves that run
+        // one copy for all (copied) inputs of the halves that run
         chunks = 1;
-        const size_t lo = do_t ? L.gt : L.reg, hi = do_p ? L.in_end : L.reg;
+        const size_t lo = do_t ? L.gt : L.cls, hi = do_p ? (pull_reg ? L.small_end : L.in_end) : L.cls;
         TFRPN_CHECK_CUDA(cudaMemcpyAsync(d + lo, pin + lo, hi - lo, cudaMemcpyHostToDevice, p->s_in));
+        p->last_h2d = (long long)(hi - lo);
         TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_gt, p->s_in));
         if (do_t) TFRPN_CHECK_CUDA(cudaStreamWaitEvent(p->s_tgt, s.ev_gt, 0));
         if (do_p) TFRPN_CHECK_CUDA(cudaStreamWaitEvent(p->s_prop, s.ev_gt, 0));
@@ -280,12 +297,20 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
                 TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_in[c], p->s_in));
                 TFRPN_CHECK_CUDA(cudaStreamWaitEvent(p->s_prop, s.ev_in[c], 0));
             }
-            if (int rc = tfrpn_proposals(h, reinterpret_cast<const float*>(d + L.reg) + (size_t)lo * N * 4,
-                                         reinterpret_cast<const float*>(d + L.cls) + (size_t)lo * N, a.anchors_dev, nb, N,
-                                         a.pcfg, reinterpret_cast<float*>(d + L.ob) + (size_t)lo * P * 4,
-                                         reinterpret_cast<float*>(d + L.os) + (size_t)lo * P,
-                                         reinterpret_cast<int32_t*>(d + L.v) + lo,
-                                         reinterpret_cast<int32_t*>(d + L.k) + (size_t)lo * P, p->s_prop)) return rc;
+            const char* reg_base = pull_reg ? pin : d;   // (pull_reg => one chunk)
+            unsigned long long* pc = nullptr;
+            if (pull_reg) {
+                pc = reinterpret_cast<unsigned long long*>(d + L.pc);
+                TFRPN_CHECK_CUDA(cudaMemsetAsync(pc, 0, 8, p->s_prop));
+                s.pulled = true; s.off_pc = L.pc;
+            }
+            if (a.pcfg->pre_nms_topn <= 0) return fail(TFRPN_ERR_BAD_ARG, "pipeline_submit: pre_nms_topn must be > 0");
+            if (int rc = proposals_enqueue(h, reinterpret_cast<const float*>(reg_base + L.reg) + (size_t)lo * N * 4,
+                                           reinterpret_cast<const float*>(d + L.cls) + (size_t)lo * N, a.anchors_dev, nb, N,
+                                           a.pcfg, reinterpret_cast<float*>(d + L.ob) + (size_t)lo * P * 4,
+                                           reinterpret_cast<float*>(d + L.os) + (size_t)lo * P,
+                                           reinterpret_cast<int32_t*>(d + L.v) + lo,
+                                           reinterpret_cast<int32_t*>(d + L.k) + (size_t)lo * P, pc, p->s_prop)) return rc;
         }
         if (do_t) {
             tfrpn_target_cfg cc = *a.tcfg;
@@ -329,7 +354,6 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         }
         TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin + lo, d + lo, hi - lo, cudaMemcpyDeviceToHost, p->s_out));
         p->last_d2h = (long long)(hi - lo);
-        p->last_h2d = (long long)((do_p ? L.in_end : L.reg) - (do_t ? L.gt : L.reg));
     }
     TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_done, p->s_out));
     s.ticket = p->next_ticket++;
@@ -425,7 +449,7 @@ extern "C" int tfrpn_pipeline_submit_acquired(tfrpn_pipeline p, const float* anc
 
 extern "C" int tfrpn_pipeline_last_copy_bytes(tfrpn_pipeline p, int64_t* h2d_bytes, int64_t* d2h_bytes) {
     if (!p || !h2d_bytes || !d2h_bytes) return fail(TFRPN_ERR_BAD_ARG, "pipeline_last_copy_bytes: null pointer");
-    *h2d_bytes = p->last_h2d;
+    *h2d_bytes = p->last_h2d + p->last_pulled;   // copy + the 16-byte rows the kernels loaded from the pinned block
     *d2h_bytes = p->last_d2h;
     return 0;
 }

@@ -20,7 +20,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tfrpn {
 
@@ -31,6 +35,24 @@ constexpr int NMS_CHUNK = 128;
 constexpr int NMS_PARTS = PR_THREADS / NMS_CHUNK;  // 8
 
 enum { MODE_TOPK = 0, MODE_NMS = 1, MODE_PROPOSALS = 2 };
+
+#ifdef TFRPN_PHASE_TIMING
+// debug build only (make EXTRA=-DTFRPN_PHASE_TIMING): cycles per phase of CTA 0, read with tfrpn_debug_phase_cycles
+__device__ long long g_phase[32];
+__device__ long long g_img[4096];   // per CTA: start clock (globaltimer ns), end, rounds
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PH_DECL __shared__ long long ph_acc[32]; __shared__ long long ph_last; \
+    if (threadIdx.x == 0) { for (int q_ = 0; q_ < 32; ++q_) ph_acc[q_] = 0; ph_last = clock64(); if (blockIdx.x < 1024) g_img[blockIdx.x * 4] = gtimer(); }
+#define PH(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); ph_acc[id] += t_ - ph_last; ph_last = t_; } } while (0)
+#define PH_FLUSH do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_img[blockIdx.x * 4 + 1] = gtimer(); \
+    if (threadIdx.x == 0 && blockIdx.x == 0) { for (int q_ = 0; q_ < 32; ++q_) g_phase[q_] = ph_acc[q_]; } } while (0)
+#else
+#define PH_DECL
+#define PH(id) do {} while (0)
+#define PH_FLUSH do {} while (0)
+#endif
+
+
 
 struct PropParams {
     int mode;
@@ -66,6 +88,7 @@ struct PropParams {
     int flag_mode;            // 0: run every image; 1: skip flagged images; 2: run flagged images only
     int* flags_out;           // NMS over a TRUNCATED candidate set: raise flags[b] when the candidates ran out
     int full_n;               //   before max_out boxes were kept and the image has more than its candidates
+    unsigned long long* rows_fetched;   // optional device counter: rows of `reg` / `boxes` the launch loaded
 };
 
 struct PropShared {
@@ -166,6 +189,7 @@ __device__ __forceinline__ unsigned long long bitonic_sort_desc(unsigned long lo
 __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     extern __shared__ float4 smem4[];
     __shared__ PropShared sh;
+    PH_DECL
     const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const int b = blockIdx.x;
     if (p.flag_mode == 1 && p.flags[b] != 0) return;
@@ -198,6 +222,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
     if (p.use_sthr) M = (int)block_sum(my_valid, &sh);
     else __syncthreads();
     const int K = min(p.k, M);  // ranks that may be consumed
+    PH(1);
     int nkept = 0;
     const IouThreshold thr = p.iou_thr;
 
@@ -259,6 +284,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
             }
             P = prefix >> shift;
         }
+        PH(2);
         // ---- 2. compaction of ranks [lo, hi) (any order: composites are unique) -----------------
         if (tid == 0) sh.count = 0u;
         sortbuf[tid] = 0ull;                    // padding sorts last
@@ -280,11 +306,13 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
             }
         }
         __syncthreads();
+        PH(3);
         // ---- 3. sort: thread t gets the composite of rank lo + t ---------------------------------
         unsigned long long mine = sortbuf[tid];
         __syncthreads();
         mine = bitonic_sort_desc(mine, sortbuf);
         const int nb = hi - lo;                 // entries in this batch
+        PH(4);
         const uint32_t my_i = 0xFFFFFFFFu - (uint32_t)(mine & 0xFFFFFFFFull);
         lo_shift = shift; lo_P = P; have_lo = true;
 
@@ -311,6 +339,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
         sidx[tid] = my_i;
         __syncthreads();
         auto fetch = [&](int pos, float4& a, float4& d, uint32_t& idx) {
+            if (p.rows_fetched && tid == 0 && pos < nb) atomicAdd(p.rows_fetched, (unsigned long long)min(NMS_CHUNK, nb - pos));
             if (tid < NMS_CHUNK && pos + tid < nb) {
                 idx = sidx[pos + tid];
                 if (p.mode == MODE_PROPOSALS) {
@@ -342,6 +371,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
             }
             if (tid < NMS_CHUNK * 4) mask32[tid] = 0u;
             __syncthreads();
+            PH(6);
             fetch(pos + NMS_CHUNK, na, nd, nidx);   // in flight during the tests below
             {   // candidates vs kept list: thread = (candidate c, part), kept j strided by NMS_PARTS
                 const int c = tid & (NMS_CHUNK - 1), part = tid >> 7;
@@ -364,6 +394,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 }
             }
             __syncthreads();
+            PH(7);
             if (warp == 0) {   // compact the candidates that survived the kept list (order preserved) into slot[]
                 int before = 0;
 #pragma unroll
@@ -377,6 +408,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 if (lane == 0) sh.nalive = before;
             }
             __syncthreads();
+            PH(8);
             {   // intra-round predecessor masks over the A survivors: bit j of row i set iff j < i and j suppresses i.
                 // The triangle is folded so that every 16-thread team gets the same number of pairs:
                 // team r takes row iA = r + 1 (iA pairs) and row iB = A - 1 - r (iB pairs) of the compact order.
@@ -393,6 +425,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 }
             }
             __syncthreads();
+            PH(9);
             if (warp == 0) {
                 // Resolve the round in parallel sweeps (same result as the sequential greedy loop):
                 // an undecided candidate is REMOVED if a kept predecessor suppresses it, KEPT if no
@@ -433,6 +466,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 if (lane == 0) sh.nk = min(before, allowed);
             }
             __syncthreads();
+            PH(10);
             if (tid < C && slot[tid] >= 0) {
                 const int s = slot[tid];
                 kbox[s] = cbox[tid];
@@ -444,6 +478,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
             }
             nkept += sh.nk;
             __syncthreads();
+            PH(11);
         }
         if (nkept >= p.max_out) break;
     }
@@ -463,11 +498,604 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
         if (p.out_classes) p.out_classes[o] = 0.0f;
     }
     if (tid == 0) p.valid[b] = nkept;
+    PH(12);
+    PH_FLUSH;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// proposal_cluster_kernel<CL>: the same algorithm with an image spread over a thread-block CLUSTER of
+// CL CTAs x (1024 / CL) threads (distributed shared memory).  The one-CTA kernel is bound by the latency
+// of its serial phases with 32 warps contending for one SM's schedulers; here every phase keeps its
+// per-thread work and runs on CL SMs, and the phases are cut so that CTAs meet as rarely as possible
+// (a cluster barrier costs ~400 cycles): two barriers per batch of ranks + ONE per NMS round.
+//
+//   scores      CTA r owns the 32-entry chunks c with c % CL == r (coalesced loads, balanced slices)
+//   select      LOCAL: every CTA radix-selects (11 bits per pass, shared-memory histogram) a threshold
+//               tau_r such that its slice holds between T/2 and T = 1024 / CL composites >= tau_r
+//               (everything when the slice has fewer), compacts them and bitonic-sorts them, one per thread
+//   merge       the sorted lists and the tau_r meet through DSMEM (barrier 1).  tau = max tau_r: every
+//               entry >= tau of the image is in some list, so the entries >= tau ARE the next ranks, in
+//               order; an entry's rank = its local rank + its lower bound in each peer's list.  Entries
+//               below tau wait for the next batch (its eligibility rule is "composite < tau").
+//   boxes       every entry's owner decodes its box and writes (canonical box, area) to slot `rank` of a
+//               replicated array in every CTA (barrier 2)
+//   NMS rounds  128 candidates per round.  The tests against the kept list AND the predecessor triangle of
+//               the round (over all its candidates: independent of the kept-list outcome) are split over
+//               all CL x T threads in one phase; the suppressed bits and the triangle rows meet through
+//               DSMEM (one barrier per round, parity-double-buffered), and every CTA resolves the round and
+//               appends to its own copy of the kept list redundantly.
+// Results are bit-identical to proposal_kernel: same composites, same order, same pair test.
+// ------------------------------------------------------------------------------------------------
+constexpr int CL_NBITS = 11;
+constexpr int CL_NB = 1 << CL_NBITS;
+constexpr int CL_MAX = 8;
+
+struct ClShared {
+    unsigned long long tau;            // this CTA's threshold of the batch (read by the peers)
+    unsigned int wtot[32], wtot2[32];
+    unsigned int digit, excl, bin_count, total;
+    unsigned int count;                // compaction cursor, then the batch's entry count
+    unsigned int valid_all[CL_MAX];    // per-CTA counts of the entries above the score threshold
+    unsigned int dead_all[2][CL_MAX][4];  // [round parity][CTA]: "suppressed by the kept list" bits
+    unsigned int dead_w[4];            // the bits found inside this CTA
+    int nk;
+};
+
+template <int CL>
+__device__ __forceinline__ void cl_sync() {
+    if (CL == 1) __syncthreads();
+    else cg::this_cluster().sync();
+}
+template <int CL, class P>
+__device__ __forceinline__ P* cl_peer(P* local, unsigned q) {
+    if (CL == 1) return local;
+    return cg::this_cluster().map_shared_rank(local, q);
+}
+
+// descending bitonic sort of S composites held by the threads t < S of the CTA, one each (all T threads call);
+// thread t < S ends with local rank t.  Strides < 32 use shuffles, the others a double-buffered shared array.
+template <int S>
+__device__ __forceinline__ unsigned long long bitonic_sort_desc_s(unsigned long long v, unsigned long long* buf) {
+    const int t = threadIdx.x;
+    const bool active = t < S;
+    int flip = 0;
+    for (int k = 2; k <= S; k <<= 1) {
+        const bool desc = (t & k) == 0;
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long pv;
+            if (j >= 32) {
+                unsigned long long* bb = buf + flip * S;
+                if (active) bb[t] = v;
+                __syncthreads();
+                pv = active ? bb[t ^ j] : 0ull;
+                flip ^= 1;
+            } else {
+                pv = __shfl_xor_sync(0xffffffffu, v, j);
+            }
+            const bool lower = (t & j) == 0;
+            const bool keep_max = (lower == desc);
+            v = keep_max ? max(v, pv) : min(v, pv);
+        }
+    }
+    return v;
+}
+
+// candidate (cb, ca) against the kept boxes j = first, first + stride, ... < nkept: four independent tests per
+// iteration (the tests are latency chains; the early exit is checked once per group)
+__device__ __forceinline__ bool kept_list_suppresses(float4 cb, float ca, const float4* kbox, const float* karea, int first,
+                                                     int stride, int nkept, const IouThreshold& thr) {
+    bool dead = false;
+    int j = first;
+    if (thr.fast) {
+        for (; j + 3 * stride < nkept && !dead; j += 4 * stride) {
+            const bool d0 = nms_suppresses_fast(cb, ca, kbox[j], karea[j], thr);
+            const bool d1 = nms_suppresses_fast(cb, ca, kbox[j + stride], karea[j + stride], thr);
+            const bool d2 = nms_suppresses_fast(cb, ca, kbox[j + 2 * stride], karea[j + 2 * stride], thr);
+            const bool d3 = nms_suppresses_fast(cb, ca, kbox[j + 3 * stride], karea[j + 3 * stride], thr);
+            dead = (d0 || d1) || (d2 || d3);
+        }
+        for (; j < nkept && !dead; j += stride) dead = nms_suppresses_fast(cb, ca, kbox[j], karea[j], thr);
+    } else {
+        for (; j < nkept && !dead; j += stride) dead = nms_suppresses(cb, ca, kbox[j], karea[j], thr);
+    }
+    return dead;
+}
+
+// CL CTAs x T threads per image; S = 1024 / CL sort slots per CTA (T >= S, T >= 128)
+template <int CL, int T>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL > 1) ? 2 : 1) proposal_cluster_kernel(PropParams p) {
+    constexpr int S = BATCH / CL;           // sort slots per CTA
+    constexpr int WARPS = T / 32;
+    constexpr int PER = CL_NB / T;          // histogram bins per thread in the scan
+    constexpr int NT = CL * T;              // threads per image
+    constexpr int PARTS = NT / NMS_CHUNK;   // kept-list parts over the whole cluster
+    constexpr int TS = NT / 64;             // threads per team of the folded triangle (64 teams)
+    static_assert(T >= S && T >= NMS_CHUNK && PER >= 1 && TS >= 1, "bad cluster shape");
+    extern __shared__ float4 smem4[];
+    __shared__ ClShared sh;
+    PH_DECL
+    const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    unsigned crank = 0;
+    if (CL > 1) crank = cg::this_cluster().block_rank();
+    const int b = blockIdx.x / CL;
+    if (p.flag_mode == 1 && p.flags[b] != 0) return;     // uniform over the cluster
+    if (p.flag_mode == 2 && p.flags[b] == 0) return;
+    const long long SN = p.N;
+    const int N = p.counts ? p.counts[b] : p.N;
+    const float* scores = p.scores + (long long)b * SN;
+    const float4* anc = p.anchors + (p.anchors_batched ? (long long)b * SN : 0LL);
+    const int* remap = p.remap ? p.remap + (long long)b * SN : nullptr;
+
+    // ---- shared memory carve -----------------------------------------------------------------------
+    unsigned int* hist = reinterpret_cast<unsigned int*>(smem4);                                 // [CL_NB]
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(hist + CL_NB);             // [CL][S]: mine, then copies of the peers'
+    unsigned long long* sortbuf = lists + BATCH;                                                 // [2][S]
+    float4* cbox_all = reinterpret_cast<float4*>(sortbuf + 2 * S);                               // [BATCH] canonical boxes by rank
+    float4* kbox = cbox_all + BATCH;                                                             // [mo_pad]
+    float* carea_all = reinterpret_cast<float*>(kbox + p.mo_pad);                                // [BATCH]
+    float* karea = carea_all + BATCH;                                                            // [mo_pad]
+    int* slot = reinterpret_cast<int*>(karea + p.mo_pad);                                        // [NMS_CHUNK]
+    unsigned int* mask32 = reinterpret_cast<unsigned int*>(slot + NMS_CHUNK);                    // [2][NMS_CHUNK][4]
+    uint32_t* skeys = mask32 + 2 * NMS_CHUNK * 4;                                                // [Lmax] when staged
+
+    // local slice: local index li <-> entry i
+    const int nchunks = (N + 31) >> 5;
+    const int Lmax = ((nchunks + CL - 1) / CL) << 5;
+    auto entry_of = [&](int li) -> int { return (((li >> 5) * CL + (int)crank) << 5) + (li & 31); };
+    auto key_at = [&](int li, int i) -> uint32_t {
+        return p.staged ? skeys[li] : score_key(scores[i], p.use_sthr, p.score_threshold);
+    };
+
+    // ---- phase 0: stage keys (four loads in flight per thread), count entries above the score threshold ----
+    unsigned int my_valid = 0;
+    for (int base = 0; base < Lmax; base += 4 * T) {
+        float sc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int li = base + u * T + tid;
+            const int i = entry_of(li);
+            sc[u] = (li < Lmax && i < N) ? __ldg(scores + i) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int li = base + u * T + tid;
+            if (li < Lmax && entry_of(li) < N) {
+                const uint32_t key = score_key(sc[u], p.use_sthr, p.score_threshold);
+                if (p.staged) skeys[li] = key;
+                my_valid += (key != 0u) ? 1u : 0u;
+            }
+        }
+    }
+    for (int k = tid; k < 2 * NMS_CHUNK * 4; k += T) mask32[k] = 0u;
+    if (tid < 4) sh.dead_w[tid] = 0u;
+    int M = N;
+    if (p.use_sthr) {
+        my_valid = __reduce_add_sync(0xffffffffu, my_valid);
+        if (lane == 0) sh.wtot[warp] = my_valid;
+        __syncthreads();
+        if (tid < CL) {
+            unsigned int tot = 0;
+            for (int w = 0; w < WARPS; ++w) tot += sh.wtot[w];
+            cl_peer<CL>(sh.valid_all + crank, (unsigned)tid)[0] = tot;
+        }
+    }
+    // (every CTA of the cluster must be running before the first remote shared-memory access)
+    cl_sync<CL>();
+    if (p.use_sthr) {
+        M = 0;
+        for (int q = 0; q < CL; ++q) M += (int)sh.valid_all[q];
+    }
+    const int K = min(p.k, M);              // ranks that may be consumed
+    int nkept = 0;
+    const IouThreshold thr = p.iou_thr;
+    PH(1);
+
+    unsigned long long lo_tau = 0ull;       // entries already consumed: composite >= lo_tau
+    bool have_lo = false;
+    int par = 0;                            // parity of the NMS round (cluster-uniform)
+
+    for (int lo = 0; lo < K;) {
+        auto eligible = [&](unsigned long long c) -> bool { return !have_lo || c < lo_tau; };
+        // ---- 1. local select: tau_r with 7S/8 <= #{eligible local composites >= tau_r} <= S (0: all of them) ----
+        unsigned long long tau_r = 0ull;
+        {
+            // leading bits every eligible key shares carry no information: the digit windows start below them
+            uint32_t kor = 0u, kand = 0xFFFFFFFFu;
+            for (int li = tid; li < Lmax; li += T) {
+                const int i = entry_of(li);
+                if (i < N) {
+                    const uint32_t key = key_at(li, i);
+                    if (eligible(make_comp(key, i))) { kor |= key; kand &= key; }
+                }
+            }
+            kor = __reduce_or_sync(0xffffffffu, kor);
+            kand = __reduce_and_sync(0xffffffffu, kand);
+            if (lane == 0) { sh.wtot[warp] = kor; sh.wtot2[warp] = kand; }
+            __syncthreads();
+            kor = 0u; kand = 0xFFFFFFFFu;
+            for (int w = 0; w < WARPS; ++w) { kor |= sh.wtot[w]; kand &= sh.wtot2[w]; }
+            __syncthreads();
+            const uint32_t diff = kor ^ kand;
+            int top = diff ? 63 - __clz(diff) : 31;                      // highest composite bit that varies
+            unsigned long long prefix = top >= 32 ? ((unsigned long long)(kand & ~((2u << (top - 32)) - 1u)) << 32)
+                                                  : ((unsigned long long)kand << 32);
+            if (kor == 0u && kand == 0xFFFFFFFFu) { top = 63; prefix = 0ull; }   // no eligible entry here
+            unsigned int r = (unsigned int)S;        // looking for the r-th largest among the entries matching `prefix`
+            for (int pass = 0; pass < 8; ++pass) {
+                const int bot = max(top - (CL_NBITS - 1), 0);
+                const int shift = bot, width = top - bot + 1;
+                for (int k = tid; k < CL_NB; k += T) hist[k] = 0u;
+                __syncthreads();
+                const unsigned long long himask = top >= 63 ? 0ull : (~0ull << (top + 1));
+                const unsigned int dmask = (1u << width) - 1u;
+                for (int li = tid; li < Lmax; li += T) {
+                    const int i = entry_of(li);
+                    if (i < N) {
+                        const unsigned long long c = make_comp(key_at(li, i), i);
+                        if (eligible(c) && ((c ^ prefix) & himask) == 0ull) atomicAdd(&hist[(unsigned)(c >> shift) & dmask], 1u);
+                    }
+                }
+                __syncthreads();
+                // thread t owns the PER digits CL_NB-1 - (t*PER + q), q = 0..PER-1, scanned from the top
+                unsigned int c[PER], s = 0;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) { c[q] = hist[CL_NB - 1 - (tid * PER + q)]; s += c[q]; }
+                const unsigned int incl_w = (unsigned int)warp_incl_scan((int)s);
+                if (lane == 31) sh.wtot[warp] = incl_w;
+                if (tid == 0) sh.bin_count = 0u;     // stays 0 when fewer than r entries match
+                __syncthreads();
+                unsigned int woff = 0, total = 0;
+                for (int w = 0; w < WARPS; ++w) {
+                    const unsigned int v = sh.wtot[w];
+                    woff += (w < warp) ? v : 0u;
+                    total += v;
+                }
+                const unsigned int excl = woff + incl_w - s;
+                if (excl < r && r <= excl + s) {
+                    unsigned int acc = excl;
+#pragma unroll
+                    for (int q = 0; q < PER; ++q) {
+                        if (acc < r && r <= acc + c[q]) {
+                            sh.digit = (unsigned)(CL_NB - 1 - (tid * PER + q));
+                            sh.excl = acc;
+                            sh.bin_count = c[q];
+                        }
+                        acc += c[q];
+                    }
+                }
+                __syncthreads();
+                const unsigned int d = sh.digit, ex = sh.excl, bc = sh.bin_count;
+                __syncthreads();
+                if (total < r) break;                                  // (first pass only) fewer than S eligible entries: all of them
+                const unsigned long long edge = prefix | ((unsigned long long)d << shift);   // lower edge of the boundary bin
+                if (bc == r - ex) { tau_r = edge; break; }             // the whole bin is taken: exactly S entries
+                if ((unsigned int)S - r + ex >= (unsigned int)(S - S / 8)) {  // leave the (small) boundary bin to the next batch
+                    tau_r = edge + (1ull << shift);
+                    break;
+                }
+                prefix = edge;
+                r -= ex;
+                top = bot - 1;                                         // (bot == 0 cannot get here: its bins are singletons)
+            }
+        }
+        PH(2);
+        // ---- 2. local compaction (<= S entries by construction): one reservation per warp -------------------
+        if (tid < S) sortbuf[tid] = 0ull;       // padding sorts last
+        if (tid == 0) sh.count = 0u;
+        __syncthreads();
+        {
+            unsigned int wtotal = 0;
+            for (int base = 0; base < Lmax; base += T) {
+                const int li = base + tid;
+                const int i = entry_of(li);
+                bool take = false;
+                if (li < Lmax && i < N) {
+                    const unsigned long long c = make_comp(key_at(li, i), i);
+                    take = eligible(c) && c >= tau_r;
+                }
+                wtotal += __popc(__ballot_sync(0xffffffffu, take));
+            }
+            unsigned int wbase = 0;
+            if (lane == 0 && wtotal != 0u) wbase = atomicAdd(&sh.count, wtotal);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (wtotal != 0u) {
+                for (int base = 0; base < Lmax; base += T) {
+                    const int li = base + tid;
+                    const int i = entry_of(li);
+                    bool take = false;
+                    unsigned long long c = 0ull;
+                    if (li < Lmax && i < N) {
+                        c = make_comp(key_at(li, i), i);
+                        take = eligible(c) && c >= tau_r;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, take);
+                    if (take) sortbuf[wbase + __popc(bal & ((1u << lane) - 1u))] = c;
+                    wbase += __popc(bal);
+                }
+            }
+        }
+        __syncthreads();
+        PH(3);
+        unsigned long long mine = tid < S ? sortbuf[tid] : 0ull;
+        __syncthreads();
+        mine = bitonic_sort_desc_s<S>(mine, sortbuf);
+        if (tid < S) lists[tid] = mine;         // my sorted list, read by the peers
+        if (tid == 0) { sh.tau = tau_r; sh.count = 0u; }
+        PH(4);
+        cl_sync<CL>();                          // barrier 1
+        // ---- 3. tau, the batch's entry count and every entry's rank ------------------------------------------
+        unsigned long long tau = tau_r;
+        if (CL > 1) {
+#pragma unroll
+            for (int q = 1; q < CL; ++q) tau = max(tau, *cl_peer<CL>(&sh.tau, (crank + q) % CL));
+        }
+        unsigned int cnt = (mine != 0ull && mine >= tau) ? 1u : 0u;
+        if (CL > 1 && tid < S) {
+#pragma unroll
+            for (int q = 1; q < CL; ++q) {
+                const unsigned long long v = cl_peer<CL>(lists, (crank + q) % CL)[tid];
+                lists[q * S + tid] = v;
+                cnt += (v != 0ull && v >= tau) ? 1u : 0u;
+            }
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0 && cnt != 0u) atomicAdd(&sh.count, cnt);
+        __syncthreads();
+        const int nb_all = (int)sh.count;                   // entries of this batch (all >= tau)
+        const int nb = min(nb_all, K - lo);                 // ... that may be consumed
+        int rank = tid;
+        if (CL > 1 && tid < S) {
+            // composites are unique (padding zeros excepted, which nobody looks at): rank = #entries greater
+#pragma unroll
+            for (int q = 1; q < CL; ++q) {
+                const unsigned long long* lst = lists + q * S;
+                int lo_i = 0, n_i = S;          // first position whose value is < mine (the list is descending)
+                while (n_i > 0) {
+                    const int half = n_i >> 1;
+                    const bool gt = lst[lo_i + half] > mine;
+                    lo_i = gt ? lo_i + half + 1 : lo_i;
+                    n_i = gt ? n_i - half - 1 : half;
+                }
+                rank += lo_i;
+            }
+        }
+        const bool real = tid < S && mine != 0ull && mine >= tau && rank < nb;
+        const uint32_t my_i = 0xFFFFFFFFu - (uint32_t)(mine & 0xFFFFFFFFull);
+        PH(5);
+
+        // ---- 4a. top-k outputs (predictor.py:58-60) -------------------------------------------------
+        if (p.mode == MODE_TOPK) {
+            if (real) {
+                const long long o = (long long)b * p.k + lo + rank;
+                p.values[o] = scores[my_i];
+                p.indices[o] = remap ? remap[my_i] : (int)my_i;
+                if (p.gathered) {
+                    if (p.reg) {
+                        float4 bx = decode_ref(ldg_f4(anc + my_i), mul4(ldg_f4(p.reg + (long long)b * SN + my_i), p.var));
+                        p.gathered[o] = p.clip_decoded ? clip01(bx) : bx;
+                    } else {
+                        p.gathered[o] = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
+                    }
+                }
+            }
+            lo += nb_all; lo_tau = tau; have_lo = true;
+            cl_sync<CL>();   // my list / tau are rewritten by the next batch while peers may still be copying them
+            continue;
+        }
+
+        // ---- 4b. boxes of the batch, replicated by rank ------------------------------------------------
+        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.rows_fetched && tid == 0 && crank == 0) atomicAdd(p.rows_fetched, (unsigned long long)nb);
+        if (real) {
+            if (p.mode == MODE_PROPOSALS) {
+                raw = decode_ref(ldg_f4(anc + my_i), mul4(ldg_f4(p.reg + (long long)b * SN + my_i), p.var));   // predictor.py:55-56
+                if (p.clip_decoded) raw = clip01(raw);
+            } else {
+                raw = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
+            }
+            float4 c = make_float4(fminf(raw.x, raw.z), fminf(raw.y, raw.w), fmaxf(raw.x, raw.z), fmaxf(raw.y, raw.w));
+            float ca = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
+            if (thr.fast && !(ca > 0.0f)) { c = TFRPN_FAR_BOX; ca = 0.0f; }   // see nms_suppresses_fast
+#pragma unroll
+            for (int q = 0; q < CL; ++q) {
+                cl_peer<CL>(cbox_all, (crank + q) % CL)[rank] = c;
+                cl_peer<CL>(carea_all, (crank + q) % CL)[rank] = ca;
+            }
+        }
+        cl_sync<CL>();                          // barrier 2
+        PH(6);
+
+        // ---- 4c. greedy NMS rounds over this batch ---------------------------------------------------
+        for (int pos = 0; pos < nb && nkept < p.max_out; pos += NMS_CHUNK, par ^= 1) {
+            const int C = min(NMS_CHUNK, nb - pos);
+            unsigned int* mk = mask32 + par * (NMS_CHUNK * 4);
+            // the other parity's mask serves the NEXT round: no peer writes to it before the barrier below
+            for (int k = tid; k < NMS_CHUNK * 4; k += T) mask32[(par ^ 1) * (NMS_CHUNK * 4) + k] = 0u;
+            const int gt = (int)crank * T + tid;
+            if (nkept > 0) {   // candidates vs kept list: thread = (candidate c, part), kept j strided by PARTS
+                const int c = gt & (NMS_CHUNK - 1), part = gt >> 7;
+                if (c < C && kept_list_suppresses(cbox_all[pos + c], carea_all[pos + c], kbox, karea, part, PARTS, nkept, thr))
+                    atomicOr(&sh.dead_w[c >> 5], 1u << (c & 31));
+            }
+            {   // predecessor masks of the round: bit j of row i set iff j < i and j suppresses i.  Folded triangle
+                // over ALL candidates of the round (independent of the kept-list outcome): TS-thread team r takes
+                // rows r + 1 and C - 1 - r
+                const int r = gt / TS, sub = gt % TS;
+                const int iA = r + 1, iB = C - 1 - r;
+                const int len = (iA < iB) ? iA + iB : (iA == iB ? iA : 0);
+                auto pair = [&](int e, int& i, int& j) -> bool {
+                    i = e < iA ? iA : iB;
+                    j = e < iA ? e : e - iA;
+                    return thr.fast ? nms_suppresses_fast(cbox_all[pos + j], carea_all[pos + j], cbox_all[pos + i], carea_all[pos + i], thr)
+                                    : nms_suppresses(cbox_all[pos + j], carea_all[pos + j], cbox_all[pos + i], carea_all[pos + i], thr);
+                };
+                int e = sub;
+                for (; e + TS < len; e += 2 * TS) {      // two independent tests in flight
+                    int i0, j0, i1, j1;
+                    const bool s0 = pair(e, i0, j0), s1 = pair(e + TS, i1, j1);
+                    if (s0) atomicOr(&mk[i0 * 4 + (j0 >> 5)], 1u << (j0 & 31));
+                    if (s1) atomicOr(&mk[i1 * 4 + (j1 >> 5)], 1u << (j1 & 31));
+                }
+                if (e < len) {
+                    int i0, j0;
+                    if (pair(e, i0, j0)) atomicOr(&mk[i0 * 4 + (j0 >> 5)], 1u << (j0 & 31));
+                }
+            }
+            __syncthreads();
+            PH(7);
+            if (tid < 4 * CL) {   // my suppressed bits -> every CTA's dead_all[par][crank]
+                const int q = tid >> 2, w = tid & 3;
+                cl_peer<CL>(&sh.dead_all[par][crank][0], (unsigned)q)[w] = sh.dead_w[w];
+            }
+            if (CL > 1) {
+                // publish the rows my teams own (rows are disjoint between CTAs): T/TS teams x 2 rows x 4 words
+                for (int k = tid; k < (T / TS) * 8; k += T) {
+                    const int team = (int)crank * (T / TS) + (k >> 3), which = (k >> 2) & 1, w = k & 3;
+                    const int rA = team + 1, rB = C - 1 - team;
+                    if (rA < rB || (rA == rB && which == 0)) {
+                        const int row = which == 0 ? rA : rB;
+                        const unsigned int v = mk[row * 4 + w];
+                        if (v != 0u) {
+#pragma unroll
+                            for (int q = 1; q < CL; ++q) cl_peer<CL>(mk, (crank + q) % CL)[row * 4 + w] = v;
+                        }
+                    }
+                }
+            }
+            cl_sync<CL>();                      // the round's barrier
+            PH(9);
+            if (warp == 0) {
+                // Resolve the round in parallel sweeps (same result as the sequential greedy loop): an undecided
+                // candidate is REMOVED if a kept predecessor suppresses it, KEPT if no undecided predecessor does,
+                // else stays undecided.  Lane l owns candidates l, 32+l, 64+l, 96+l, so ballot word q is exactly
+                // bits [32q, 32q+32).  Candidates suppressed by the kept list are in neither set.
+                const uint4* m4 = reinterpret_cast<const uint4*>(mk);
+                uint4 pr[4];
+                unsigned U[4], Kp[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    pr[q] = m4[q * 32 + lane];
+                    unsigned dead_w = 0u;
+                    if (nkept > 0) {
+#pragma unroll
+                        for (int g = 0; g < CL; ++g) dead_w |= sh.dead_all[par][g][q];
+                    }
+                    U[q] = __ballot_sync(0xffffffffu, q * 32 + lane < C) & ~dead_w;
+                }
+                while ((U[0] | U[1] | U[2] | U[3]) != 0u) {
+                    unsigned nU[4], nK[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool und = (U[q] >> lane) & 1u;
+                        const unsigned hitK = (pr[q].x & Kp[0]) | (pr[q].y & Kp[1]) | (pr[q].z & Kp[2]) | (pr[q].w & Kp[3]);
+                        const unsigned hitU = (pr[q].x & U[0]) | (pr[q].y & U[1]) | (pr[q].z & U[2]) | (pr[q].w & U[3]);
+                        nK[q] = __ballot_sync(0xffffffffu, und && hitK == 0u && hitU == 0u);
+                        nU[q] = __ballot_sync(0xffffffffu, und && hitK == 0u && hitU != 0u);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { Kp[q] |= nK[q]; U[q] = nU[q]; }
+                }
+                // kept candidates take consecutive output slots in score order, capped at max_out
+                const int allowed = p.max_out - nkept;
+                int before = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rk = before + __popc(Kp[q] & ((1u << lane) - 1u));
+                    const bool kept = ((Kp[q] >> lane) & 1u) && rk < allowed;
+                    slot[q * 32 + lane] = kept ? nkept + rk : -1;
+                    before += __popc(Kp[q]);
+                }
+                if (lane == 0) sh.nk = min(before, allowed);
+                if (lane < 4) sh.dead_w[lane] = 0u;
+            }
+            __syncthreads();
+            PH(10);
+            if (tid < C && slot[tid] >= 0) {      // every CTA appends to its own copy of the kept list
+                const int s = slot[tid];
+                kbox[s] = cbox_all[pos + tid];
+                karea[s] = carea_all[pos + tid];
+            }
+            if (real && rank >= pos && rank < pos + C) {   // the owner of a kept candidate writes its outputs
+                const int s = slot[rank - pos];
+                if (s >= 0) {
+                    const long long o = (long long)b * p.rows + s;
+                    p.out_boxes[o] = p.clip_out ? clip01(raw) : raw;
+                    p.out_scores[o] = scores[my_i];
+                    if (p.keep_idx) p.keep_idx[o] = remap ? remap[my_i] : (int)my_i;
+                }
+            }
+            nkept += sh.nk;
+            __syncthreads();
+            PH(11);
+        }
+        lo += nb_all; lo_tau = tau; have_lo = true;
+        if (nkept >= p.max_out) break;
+    }
+    if (CL > 1) cg::this_cluster().sync();   // no CTA leaves while a peer may still access its shared memory
+    if (p.mode == MODE_TOPK) return;
+    if (p.flags_out && nkept < p.max_out && N < p.full_n) {   // the unfiltered kernel redoes this image
+        if (tid == 0 && crank == 0) p.flags_out[b] = 1;
+        return;
+    }
+    // zero padding (TF pads boxes/scores/classes with 0); keep_idx pads with -1
+    for (int rnk = (int)crank * T + tid; rnk < p.rows; rnk += NT) {
+        const long long o = (long long)b * p.rows + rnk;
+        if (rnk >= nkept) {
+            p.out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+            p.out_scores[o] = 0.0f;
+            if (p.keep_idx) p.keep_idx[o] = -1;
+        }
+        if (p.out_classes) p.out_classes[o] = 0.0f;
+    }
+    if (tid == 0 && crank == 0) p.valid[b] = nkept;
+    PH(12);
+    PH_FLUSH;
+}
+
+static size_t cluster_smem_bytes(int cl, int n_staged, int max_out) {
+    max_out = (max_out + 3) & ~3;
+    const int T = 1024 / cl;                        // (sort slots per CTA)
+    const int nchunks = (n_staged + 31) / 32;
+    const size_t lmax = (size_t)((nchunks + cl - 1) / cl) * 32;
+    size_t s = (size_t)CL_NB * 4;                   // histogram
+    s += (size_t)BATCH * 8;                         // my sorted list + the peers'
+    s += (size_t)2 * T * 8;                         // sortbuf (double buffer)
+    s += (size_t)(BATCH + max_out) * (16 + 4);      // boxes + areas: batch by rank, kept list
+    s += (size_t)NMS_CHUNK * (4 + 2 * 16);          // slot, mask32 (two parities)
+    s += lmax * 4;                                  // staged score keys of the slice
+    return s + 16;
 }
 
 int set_attributes_proposals() {
-    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 4096)));
+    const int lim = (int)(227 * 1024 - 4096);
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_cluster_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_cluster_kernel<2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_cluster_kernel<2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_cluster_kernel<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_cluster_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_cluster_kernel<8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    TFRPN_CHECK_CUDA(cudaFuncSetAttribute(proposal_cluster_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     return 0;
+}
+
+// Shape of the proposal stage for a batch of B images (measured, profiles/r2c_prop_shapes.txt): total threads
+// around 64 k is the sweet spot -- B <= 32: 8 CTAs x 256 threads per image; B <= 95: 2 CTAs x 512; larger batches
+// fill the GPU with one 1024-thread CTA per image (proposal_kernel).  TFRPN_PROP_CLUSTER = 10 * t + cl forces a
+// shape (A/B switch): cl = 0 one-CTA kernel, 1 / 2 / 4 / 8 CTAs per image; t selects the threads per CTA.
+static void pick_cluster(tfrpn_handle h, int B, int& cl, int& threads) {
+    const int v = h->opts.prop_cluster;
+    if (v >= 0) {
+        cl = v % 10;
+        const int t = v / 10;
+        if (cl != 1 && cl != 2 && cl != 4 && cl != 8) { cl = 0; threads = 1024; return; }
+        threads = cl == 1 ? 1024 : cl == 2 ? (t == 1 ? 512 : 1024) : cl == 4 ? (t == 1 ? 256 : 512) : (t == 2 ? 512 : 256);
+        return;
+    }
+    if (B <= 32) { cl = 8; threads = 256; }
+    else if (B <= 95) { cl = 2; threads = 512; }
+    else { cl = 0; threads = 1024; }
 }
 
 static IouThreshold make_threshold(float thr) {
@@ -798,6 +1426,26 @@ static int launch(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
 
 static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
     p.mo_pad = (p.max_out + 3) & ~3;
+    int cl = 0, threads = 1024;
+    pick_cluster(h, B, cl, threads);
+    if (cl) {
+        p.staged = cluster_smem_bytes(cl, p.N, p.max_out) <= PROP_SMEM_LIMIT ? 1 : 0;
+        const size_t smem = cluster_smem_bytes(cl, p.staged ? p.N : 0, p.max_out);
+        if (smem > PROP_SMEM_LIMIT)
+            return fail(TFRPN_ERR_UNSUPPORTED, "NMS: %d output rows need %zu B of shared memory (> %zu)", p.max_out, smem,
+                        PROP_SMEM_LIMIT);
+        prof_begin(h, TFRPN_K_PROPOSAL, st);
+        if (cl == 8 && threads == 512) proposal_cluster_kernel<8, 512><<<B * 8, 512, smem, st>>>(p);
+        else if (cl == 8) proposal_cluster_kernel<8, 256><<<B * 8, 256, smem, st>>>(p);
+        else if (cl == 4 && threads == 256) proposal_cluster_kernel<4, 256><<<B * 4, 256, smem, st>>>(p);
+        else if (cl == 4) proposal_cluster_kernel<4, 512><<<B * 4, 512, smem, st>>>(p);
+        else if (cl == 2 && threads == 512) proposal_cluster_kernel<2, 512><<<B * 2, 512, smem, st>>>(p);
+        else if (cl == 2) proposal_cluster_kernel<2, 1024><<<B * 2, 1024, smem, st>>>(p);
+        else proposal_cluster_kernel<1, 1024><<<B, 1024, smem, st>>>(p);
+        prof_end(h, st);
+        TFRPN_AFTER_LAUNCH("proposal_cluster_kernel");
+        return 0;
+    }
     p.staged = prop_smem_bytes(p.N, p.max_out) <= PROP_SMEM_LIMIT ? 1 : 0;
     const size_t smem = prop_smem_bytes(p.staged ? p.N : 0, p.max_out);
     if (smem > PROP_SMEM_LIMIT)
@@ -884,6 +1532,27 @@ extern "C" int tfrpn_nms(tfrpn_handle h, const float* boxes, const float* scores
     return launch(h, p, B, as_stream(s));
 }
 
+namespace tfrpn {
+// The fused stage after argument checks.  `rpn_reg` may also be PAGE-LOCKED HOST memory (pipeline.cu): the kernels
+// touch only the rows of the candidates they examine (<= ~1000 of the N rows per image), so those rows are
+// pulled over PCIe by the loads themselves instead of copying the whole tensor to the device first.
+int proposals_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B, int N,
+                      const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
+                      int32_t* keep_idx_or_null, unsigned long long* rows_fetched_or_null, cudaStream_t st) {
+    PropParams p = {};
+    p.rows_fetched = rows_fetched_or_null;
+    p.mode = MODE_PROPOSALS; p.N = N; p.k = min(cfg->pre_nms_topn, N); p.scores = rpn_cls; p.use_sthr = 0;
+    p.reg = reinterpret_cast<const float4*>(rpn_reg); p.anchors = reinterpret_cast<const float4*>(anchors);
+    p.var = make_float4(cfg->variances[0], cfg->variances[1], cfg->variances[2], cfg->variances[3]);
+    p.clip_decoded = cfg->clip;
+    p.rows = cfg->post_nms_topn; p.max_out = cfg->post_nms_topn;
+    p.iou_thr = make_threshold(cfg->nms_iou_threshold); p.clip_out = 1;  // combined NMS default clip_boxes=True
+    p.out_boxes = reinterpret_cast<float4*>(out_boxes); p.out_scores = out_scores; p.out_classes = nullptr;
+    p.valid = valid; p.keep_idx = keep_idx_or_null;
+    return launch(h, p, B, st);
+}
+}  // namespace tfrpn
+
 extern "C" int tfrpn_proposals(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B,
                                int N, const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores,
                                int32_t* valid, int32_t* keep_idx_or_null, tfrpn_stream s) {
@@ -897,14 +1566,15 @@ extern "C" int tfrpn_proposals(tfrpn_handle h, const float* rpn_reg, const float
     if (!h) return fail(TFRPN_ERR_BAD_ARG, "proposals: null handle");
     TFRPN_ENTER(h);
     TFRPN_CHECK_ON_DEVICE(h, rpn_reg, "proposals: rpn_reg");
-    PropParams p = {};
-    p.mode = MODE_PROPOSALS; p.N = N; p.k = min(cfg->pre_nms_topn, N); p.scores = rpn_cls; p.use_sthr = 0;
-    p.reg = reinterpret_cast<const float4*>(rpn_reg); p.anchors = reinterpret_cast<const float4*>(anchors);
-    p.var = make_float4(cfg->variances[0], cfg->variances[1], cfg->variances[2], cfg->variances[3]);
-    p.clip_decoded = cfg->clip;
-    p.rows = cfg->post_nms_topn; p.max_out = cfg->post_nms_topn;
-    p.iou_thr = make_threshold(cfg->nms_iou_threshold); p.clip_out = 1;  // combined NMS default clip_boxes=True
-    p.out_boxes = reinterpret_cast<float4*>(out_boxes); p.out_scores = out_scores; p.out_classes = nullptr;
-    p.valid = valid; p.keep_idx = keep_idx_or_null;
-    return launch(h, p, B, as_stream(s));
+    return proposals_enqueue(h, rpn_reg, rpn_cls, anchors, B, N, cfg, out_boxes, out_scores, valid, keep_idx_or_null,
+                             nullptr, as_stream(s));
 }
+
+#ifdef TFRPN_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int tfrpn_debug_phase_cycles(long long* out32) {
+    return cudaMemcpyFromSymbol(out32, tfrpn::g_phase, sizeof(long long) * 32) == cudaSuccess ? 0 : -3;
+}
+extern "C" __attribute__((visibility("default"))) int tfrpn_debug_cta_times(long long* out4096) {
+    return cudaMemcpyFromSymbol(out4096, tfrpn::g_img, sizeof(long long) * 4096) == cudaSuccess ? 0 : -3;
+}
+#endif
