@@ -300,6 +300,10 @@ TFRPN_API int tfrpn_pipeline_wait(tfrpn_pipeline p, int64_t ticket);
 /* bytes the last submitted acquired step copies in each direction (bbox_deltas travels in compact form,
  * see tfrpn_rpn_targets_compact, and is expanded into the slot's dense host array by wait()) */
 TFRPN_API int tfrpn_pipeline_last_copy_bytes(tfrpn_pipeline p, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* Tracing (handles created with TFRPN_PIPE_TRACE=1 in the environment): device time stamps of step `ticket`, ms
+ * since the pipeline was created -- [0,1] H2D begin/end, [2,3] target kernels, [4,5] proposal kernels, [6,7] D2H.
+ * Valid after wait(ticket) until the slot's next step is retired. */
+TFRPN_API int tfrpn_pipeline_trace(tfrpn_pipeline p, int64_t ticket, float* ms8);
 TFRPN_API int tfrpn_pipeline_drain(tfrpn_pipeline p); /* wait for every step in flight */
 TFRPN_API int tfrpn_pipeline_destroy(tfrpn_pipeline p);
 /* page-locked host memory for the caller's batches (so H2D/D2H run at full PCIe rate) */

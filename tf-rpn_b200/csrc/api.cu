@@ -178,6 +178,7 @@ extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
     h->opts.pipe_chunks = env_int("TFRPN_PIPE_CHUNKS", 0);
     h->opts.prop_cluster = env_int("TFRPN_PROP_CLUSTER", -1);
     h->opts.pipe_dense_in = getenv("TFRPN_PIPE_DENSE_IN") != nullptr;
+    h->opts.pipe_trace = getenv("TFRPN_PIPE_TRACE") != nullptr;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     // device counter of the loss reduction (losses.cu): zero between calls, the kernel resets it
     if (cudaMalloc(&h->ticket, 256) != cudaSuccess || cudaMemset(h->ticket, 0, 256) != cudaSuccess) {

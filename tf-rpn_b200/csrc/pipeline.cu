@@ -52,6 +52,9 @@ struct Slot {
     cudaEvent_t ev_gt = nullptr, ev_prop = nullptr, ev_done = nullptr;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_tgt[MAX_CHUNKS] = {};
     long long ticket = -1;          // ticket in flight in this slot (-1 = free)
+    cudaEvent_t tr[8] = {};         // TFRPN_PIPE_TRACE: timing events (h2d, targets, proposals, d2h: begin / end)
+    float tr_ms[8] = {};            // ... of the last step retired from this slot, ms since the pipeline was created
+    long long tr_ticket = -1;
     // compact results (acquired mode): bbox_deltas comes back as its <= total_pos non-zero rows per image and is
     // expanded into the slot's dense host array when the step is retired (the labels travel as they are)
     bool pulled = false;            // the step in flight pulls rpn_reg rows from the pinned block (row count at off_pc)
@@ -75,6 +78,8 @@ struct tfrpn_pipe {
     int depth = 1;
     cudaStream_t s_in = nullptr, s_tgt = nullptr, s_prop = nullptr, s_out = nullptr;
     cudaEvent_t ev_after = nullptr;
+    bool trace = false;             // TFRPN_PIPE_TRACE=1 (read when the handle was created)
+    cudaEvent_t ev_base = nullptr;  // time origin of the trace
     Slot slots[MAX_DEPTH];
     long long next_ticket = 0;
     int acq_B = 0, acq_N = 0, acq_G = 0, acq_P = 0;   // shape of the slot handed out by the last acquire()
@@ -91,11 +96,13 @@ void pipe_destroy(tfrpn_pipe* p) {
     for (cudaStream_t s : {p->s_in, p->s_tgt, p->s_prop, p->s_out})
         if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     if (p->ev_after) cudaEventDestroy(p->ev_after);
+    if (p->ev_base) cudaEventDestroy(p->ev_base);
     for (int i = 0; i < p->depth; ++i) {
         Slot& s = p->slots[i];
         if (s.dev) cudaFree(s.dev);
         if (s.pin) cudaFreeHost(s.pin);
         for (cudaEvent_t e : {s.ev_gt, s.ev_prop, s.ev_done}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : s.tr) if (e) cudaEventDestroy(e);
         for (int c = 0; c < MAX_CHUNKS; ++c) {
             if (s.ev_in[c]) cudaEventDestroy(s.ev_in[c]);
             if (s.ev_tgt[c]) cudaEventDestroy(s.ev_tgt[c]);
@@ -125,6 +132,13 @@ static int pipe_create(tfrpn_handle h, int depth, tfrpn_pipe** out) {
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.ev_tgt[c], cudaEventDisableTiming);
         }
     }
+    p->trace = h->opts.pipe_trace;
+    if (p->trace && e == cudaSuccess) {
+        e = cudaEventCreate(&p->ev_base);
+        if (e == cudaSuccess) e = cudaEventRecord(p->ev_base, p->s_in);
+        for (int i = 0; i < depth; ++i)
+            for (cudaEvent_t& ev : p->slots[i].tr) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    }
     if (e != cudaSuccess) { pipe_destroy(p); return cuda_fail(e, "pipeline_create"); }
     *out = p;
     return 0;
@@ -134,6 +148,11 @@ static int pipe_create(tfrpn_handle h, int depth, tfrpn_pipe** out) {
 static int slot_finish(tfrpn_pipe* p, Slot& s) {
     if (s.ticket < 0) return 0;
     TFRPN_CHECK_CUDA(cudaEventSynchronize(s.ev_done));
+    if (p->trace) {
+        for (int i = 0; i < 8; ++i)
+            if (cudaEventElapsedTime(&s.tr_ms[i], p->ev_base, s.tr[i]) != cudaSuccess) { s.tr_ms[i] = -1.0f; cudaGetLastError(); }
+        s.tr_ticket = s.ticket;
+    }
     for (int i = 0; i < s.n_copies; ++i) memcpy(s.copies[i].dst, s.copies[i].src, s.copies[i].bytes);
     s.n_copies = 0;
     if (s.pulled) {
@@ -255,6 +274,9 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         for (cudaStream_t st : {p->s_in, p->s_tgt, p->s_prop, p->s_out}) TFRPN_CHECK_CUDA(cudaStreamWaitEvent(st, p->ev_after, 0));
     }
     s.n_copies = 0;
+    auto mark = [&](int i, cudaStream_t st) { if (p->trace) cudaEventRecord(s.tr[i], st); };
+    if (p->trace) for (int i = 0; i < 8; ++i) cudaEventRecord(s.tr[i], p->s_in);   // halves that do not run read as 0-length
+    mark(0, p->s_in);
     // Acquired slots return bbox_deltas in compact form (2.8 MB of results instead of 11.5 MB per C2 step: the
     // deltas are exactly zero outside the <= total_pos sampled positives, utils/train_utils.py:137);
     // slot_finish expands them into the slot's dense host array.
@@ -278,9 +300,12 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         const size_t lo = do_t ? L.gt : L.cls, hi = do_p ? (pull_reg ? L.small_end : L.in_end) : L.cls;
         TFRPN_CHECK_CUDA(cudaMemcpyAsync(d + lo, pin + lo, hi - lo, cudaMemcpyHostToDevice, p->s_in));
         p->last_h2d = (long long)(hi - lo);
+        mark(1, p->s_in);
         TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_gt, p->s_in));
         if (do_t) TFRPN_CHECK_CUDA(cudaStreamWaitEvent(p->s_tgt, s.ev_gt, 0));
         if (do_p) TFRPN_CHECK_CUDA(cudaStreamWaitEvent(p->s_prop, s.ev_gt, 0));
+        if (do_t) mark(2, p->s_tgt);
+        if (do_p) mark(4, p->s_prop);
     } else if (do_t) {
         if (int rc = h2d(L.gt, a.gt_boxes, (size_t)B * G * 16)) return rc;
         if (int rc = h2d(L.gl, a.gt_labels, (size_t)B * G * 4)) return rc;
@@ -324,6 +349,7 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
                                            reinterpret_cast<const int32_t*>(d + L.gl) + (size_t)lo * G, nb, N, G, &cc,
                                            reinterpret_cast<float*>(d + L.d) + (size_t)lo * N * 4,
                                            reinterpret_cast<float*>(d + L.l) + (size_t)lo * N, nullptr, p->s_tgt)) return rc;
+            mark(3, p->s_tgt);
             TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_tgt[c], p->s_tgt));
             TFRPN_CHECK_CUDA(cudaStreamWaitEvent(p->s_out, s.ev_tgt[c], 0));
             if (!acquired) {
@@ -333,6 +359,7 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         }
     }
     if (do_p) {
+        mark(5, p->s_prop);
         TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_prop, p->s_prop));
         TFRPN_CHECK_CUDA(cudaStreamWaitEvent(p->s_out, s.ev_prop, 0));
         if (!acquired) {
@@ -352,9 +379,11 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
             s.compact = true; s.cB = B; s.cN = N; s.cTP = a.tcfg->total_pos;
             s.off_d = L.d; s.off_ci = L.ci; s.off_cd = L.cd;
         }
+        mark(6, p->s_out);
         TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin + lo, d + lo, hi - lo, cudaMemcpyDeviceToHost, p->s_out));
         p->last_d2h = (long long)(hi - lo);
     }
+    mark(7, p->s_out);
     TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_done, p->s_out));
     s.ticket = p->next_ticket++;
     if (ticket_out) *ticket_out = s.ticket;
@@ -451,6 +480,15 @@ extern "C" int tfrpn_pipeline_last_copy_bytes(tfrpn_pipeline p, int64_t* h2d_byt
     if (!p || !h2d_bytes || !d2h_bytes) return fail(TFRPN_ERR_BAD_ARG, "pipeline_last_copy_bytes: null pointer");
     *h2d_bytes = p->last_h2d + p->last_pulled;   // copy + the 16-byte rows the kernels loaded from the pinned block
     *d2h_bytes = p->last_d2h;
+    return 0;
+}
+
+extern "C" int tfrpn_pipeline_trace(tfrpn_pipeline p, int64_t ticket, float* ms8) {
+    if (!p || !ms8) return fail(TFRPN_ERR_BAD_ARG, "pipeline_trace: null pointer");
+    if (!p->trace) return fail(TFRPN_ERR_UNSUPPORTED, "pipeline_trace: the handle was created without TFRPN_PIPE_TRACE=1");
+    const Slot& s = p->slots[(ticket < 0 ? 0 : ticket) % p->depth];
+    if (s.tr_ticket != ticket) return fail(TFRPN_ERR_BAD_ARG, "pipeline_trace: step %lld is not the last one retired from its slot", (long long)ticket);
+    for (int i = 0; i < 8; ++i) ms8[i] = s.tr_ms[i];
     return 0;
 }
 

@@ -5,7 +5,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libtfrpn_cuda.so")
+# TFRPN_LIB_PATH: a debug build of the same library (tools/phase_times.py); the product path is the in-tree .so
+LIB_PATH = os.environ.get("TFRPN_LIB_PATH") or os.path.join(_HERE, "_lib", "libtfrpn_cuda.so")
 
 
 class AnchorCfg(C.Structure):
@@ -89,6 +90,7 @@ PROTOTYPES = {
     "tfrpn_pipeline_submit_acquired": (I, [P, P, C.POINTER(TargetCfg), C.POINTER(ProposalCfg), C.POINTER(C.c_int64)]),
     "tfrpn_pipeline_wait": (I, [P, C.c_int64]),
     "tfrpn_pipeline_last_copy_bytes": (I, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "tfrpn_pipeline_trace": (I, [P, C.c_int64, C.POINTER(C.c_float)]),
     "tfrpn_pipeline_drain": (I, [P]),
     "tfrpn_pipeline_destroy": (I, [P]),
     "tfrpn_host_alloc": (I, [C.POINTER(P), C.c_size_t]),
