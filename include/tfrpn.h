@@ -266,7 +266,7 @@ TFRPN_API int tfrpn_rpn_step_host(tfrpn_handle h, const float* anchors_dev,
  *      copied directly, others through the slot's pinned staging.  While steps are in flight the
  *      handle's workspace belongs to the pipeline: do not call tfrpn_rpn_targets on it concurrently. */
 typedef struct tfrpn_pipe* tfrpn_pipeline;
-TFRPN_API int tfrpn_pipeline_create(tfrpn_handle h, int depth /* 1..8 */, tfrpn_pipeline* out);
+TFRPN_API int tfrpn_pipeline_create(tfrpn_handle h, int depth /* 1..16 */, tfrpn_pipeline* out);
 TFRPN_API int tfrpn_pipeline_submit(tfrpn_pipeline p, const float* anchors_dev /* (N,4) device */, int B, int N,
                           const float* gt_boxes_host, const int32_t* gt_labels_host, int G,
                           const tfrpn_target_cfg* tcfg, float* deltas_host, float* labels_host,
@@ -301,9 +301,10 @@ TFRPN_API int tfrpn_pipeline_wait(tfrpn_pipeline p, int64_t ticket);
  * see tfrpn_rpn_targets_compact, and is expanded into the slot's dense host array by wait()) */
 TFRPN_API int tfrpn_pipeline_last_copy_bytes(tfrpn_pipeline p, int64_t* h2d_bytes, int64_t* d2h_bytes);
 /* Tracing (handles created with TFRPN_PIPE_TRACE=1 in the environment): device time stamps of step `ticket`, ms
- * since the pipeline was created -- [0,1] H2D begin/end, [2,3] target kernels, [4,5] proposal kernels, [6,7] D2H.
- * Valid after wait(ticket) until the slot's next step is retired. */
-TFRPN_API int tfrpn_pipeline_trace(tfrpn_pipeline p, int64_t ticket, float* ms8);
+ * since the pipeline was created -- [0,1] H2D begin/end, [2,3] target kernels, [4,5] proposal stage (rank launch,
+ * host gather, NMS launch), [6,7] D2H + expansion; then host durations in ms: [8] the row gather, [9] the
+ * expansion of the compact bbox_deltas.  Valid after wait(ticket) until the slot's next step is retired. */
+TFRPN_API int tfrpn_pipeline_trace(tfrpn_pipeline p, int64_t ticket, float* ms10);
 TFRPN_API int tfrpn_pipeline_drain(tfrpn_pipeline p); /* wait for every step in flight */
 TFRPN_API int tfrpn_pipeline_destroy(tfrpn_pipeline p);
 /* page-locked host memory for the caller's batches (so H2D/D2H run at full PCIe rate) */

@@ -34,7 +34,7 @@ constexpr int BATCH = PR_THREADS;   // ranks sorted per batch: one composite per
 constexpr int NMS_CHUNK = 128;
 constexpr int NMS_PARTS = PR_THREADS / NMS_CHUNK;  // 8
 
-enum { MODE_TOPK = 0, MODE_NMS = 1, MODE_PROPOSALS = 2 };
+enum { MODE_TOPK = 0, MODE_NMS = 1, MODE_PROPOSALS = 2, MODE_RANK = 3 };
 
 #ifdef TFRPN_PHASE_TIMING
 // debug build only (make EXTRA=-DTFRPN_PHASE_TIMING): cycles per phase of CTA 0, read with tfrpn_debug_phase_cycles
@@ -89,7 +89,17 @@ struct PropParams {
     int* flags_out;           // NMS over a TRUNCATED candidate set: raise flags[b] when the candidates ran out
     int full_n;               //   before max_out boxes were kept and the image has more than its candidates
     unsigned long long* rows_fetched;   // optional device counter: rows of `reg` / `boxes` the launch loaded
-};
+    // two-phase flow (pipeline.cu, cluster kernel only): a MODE_RANK launch writes the first batch of ranks of every
+    // image; the host gathers those rows of `reg`; a `presorted` launch then runs NMS over that batch alone.
+    int* rank_idx;              // MODE_RANK out / presorted in: (B, BATCH) entry index by rank
+    int* rank_n;                // (B,) ranks in the batch
+    int* rank_more;             // (B,) 1: ranks beyond the batch exist and may be consumed
+    int presorted;
+    const float4* reg_compact;  // presorted: rows of `reg` in rank order, (B, compact_stride); null: read `reg`
+    int compact_rows;           //   ranks >= compact_rows read `reg`, or end the batch when `reg` is null
+    int compact_stride;
+    int* redo_flags;            // presorted out (B,): 1 = the batch ran out before max_out boxes were kept (the
+};                              //   unfiltered kernel must redo the image), else 0
 
 struct PropShared {
     unsigned int hist[256];
@@ -649,7 +659,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
 
     // ---- phase 0: stage keys (four loads in flight per thread), count entries above the score threshold ----
     unsigned int my_valid = 0;
-    for (int base = 0; base < Lmax; base += 4 * T) {
+    for (int base = 0; base < Lmax && !p.presorted; base += 4 * T) {
         float sc[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -686,7 +696,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
         M = 0;
         for (int q = 0; q < CL; ++q) M += (int)sh.valid_all[q];
     }
-    const int K = min(p.k, M);              // ranks that may be consumed
+    int K = min(p.k, M);                    // ranks that may be consumed
+    bool cut = false;                       // presorted: the launch cannot serve every rank of the batch
+    if (p.presorted) {
+        K = p.rank_n[b];
+        if (p.reg_compact && K > p.compact_rows) { K = p.compact_rows; cut = true; }   // only the gathered rows are served
+    }
     int nkept = 0;
     const IouThreshold thr = p.iou_thr;
     PH(1);
@@ -697,6 +712,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
 
     for (int lo = 0; lo < K;) {
         auto eligible = [&](unsigned long long c) -> bool { return !have_lo || c < lo_tau; };
+        unsigned long long mine = 0ull, tau = 0ull;
+        int nb_all = K, nb = K, rank = (int)crank * S + tid;     // presorted: thread t of CTA r owns rank r * S + t
+        if (!p.presorted) {
         // ---- 1. local select: tau_r with 7S/8 <= #{eligible local composites >= tau_r} <= S (0: all of them) ----
         unsigned long long tau_r = 0ull;
         {
@@ -817,7 +835,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
         }
         __syncthreads();
         PH(3);
-        unsigned long long mine = tid < S ? sortbuf[tid] : 0ull;
+        mine = tid < S ? sortbuf[tid] : 0ull;
         __syncthreads();
         mine = bitonic_sort_desc_s<S>(mine, sortbuf);
         if (tid < S) lists[tid] = mine;         // my sorted list, read by the peers
@@ -825,7 +843,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
         PH(4);
         cl_sync<CL>();                          // barrier 1
         // ---- 3. tau, the batch's entry count and every entry's rank ------------------------------------------
-        unsigned long long tau = tau_r;
+        tau = tau_r;
         if (CL > 1) {
 #pragma unroll
             for (int q = 1; q < CL; ++q) tau = max(tau, *cl_peer<CL>(&sh.tau, (crank + q) % CL));
@@ -842,9 +860,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0 && cnt != 0u) atomicAdd(&sh.count, cnt);
         __syncthreads();
-        const int nb_all = (int)sh.count;                   // entries of this batch (all >= tau)
-        const int nb = min(nb_all, K - lo);                 // ... that may be consumed
-        int rank = tid;
+        nb_all = (int)sh.count;                             // entries of this batch (all >= tau)
+        nb = min(nb_all, K - lo);                           // ... that may be consumed
+        rank = tid;
         if (CL > 1 && tid < S) {
             // composites are unique (padding zeros excepted, which nobody looks at): rank = #entries greater
 #pragma unroll
@@ -860,9 +878,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
                 rank += lo_i;
             }
         }
-        const bool real = tid < S && mine != 0ull && mine >= tau && rank < nb;
-        const uint32_t my_i = 0xFFFFFFFFu - (uint32_t)(mine & 0xFFFFFFFFull);
+        }   // !presorted
+        const bool real = p.presorted ? (tid < S && rank < nb) : (tid < S && mine != 0ull && mine >= tau && rank < nb);
+        const uint32_t my_i = p.presorted ? (real ? (uint32_t)p.rank_idx[(long long)b * BATCH + rank] : 0u)
+                                          : 0xFFFFFFFFu - (uint32_t)(mine & 0xFFFFFFFFull);
         PH(5);
+        if (p.mode == MODE_RANK) {   // the first batch is all this launch computes
+            if (real) p.rank_idx[(long long)b * BATCH + rank] = (int)my_i;
+            if (tid == 0 && crank == 0) { p.rank_n[b] = nb; p.rank_more[b] = (nb_all < K) ? 1 : 0; }
+            break;
+        }
 
         // ---- 4a. top-k outputs (predictor.py:58-60) -------------------------------------------------
         if (p.mode == MODE_TOPK) {
@@ -886,10 +911,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
 
         // ---- 4b. boxes of the batch, replicated by rank ------------------------------------------------
         float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.rows_fetched && tid == 0 && crank == 0) atomicAdd(p.rows_fetched, (unsigned long long)nb);
+        if (p.rows_fetched && tid == 0 && crank == 0)
+            atomicAdd(p.rows_fetched, (unsigned long long)((p.presorted && p.reg_compact) ? max(nb - p.compact_rows, 0) : nb));
         if (real) {
             if (p.mode == MODE_PROPOSALS) {
-                raw = decode_ref(ldg_f4(anc + my_i), mul4(ldg_f4(p.reg + (long long)b * SN + my_i), p.var));   // predictor.py:55-56
+                const float4 row = (p.presorted && p.reg_compact && rank < p.compact_rows)
+                                       ? ldg_f4(p.reg_compact + (long long)b * p.compact_stride + rank)
+                                       : ldg_f4(p.reg + (long long)b * SN + my_i);
+                raw = decode_ref(ldg_f4(anc + my_i), mul4(row, p.var));   // predictor.py:55-56
                 if (p.clip_decoded) raw = clip01(raw);
             } else {
                 raw = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
@@ -1033,7 +1062,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
         if (nkept >= p.max_out) break;
     }
     if (CL > 1) cg::this_cluster().sync();   // no CTA leaves while a peer may still access its shared memory
-    if (p.mode == MODE_TOPK) return;
+    if (p.mode == MODE_TOPK || p.mode == MODE_RANK) return;
+    if (p.presorted) {
+        const bool redo = nkept < p.max_out && (cut || p.rank_more[b] != 0);
+        if (tid == 0 && crank == 0) p.redo_flags[b] = redo ? 1 : 0;
+        if (redo) return;
+    }
     if (p.flags_out && nkept < p.max_out && N < p.full_n) {   // the unfiltered kernel redoes this image
         if (tid == 0 && crank == 0) p.flags_out[b] = 1;
         return;
@@ -1424,12 +1458,11 @@ static int launch(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
     return launch_one(h, p, B, st);
 }
 
-static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
+static int launch_cluster(tfrpn_handle h, PropParams& p, int B, int cl, int threads, cudaStream_t st) {
     p.mo_pad = (p.max_out + 3) & ~3;
-    int cl = 0, threads = 1024;
-    pick_cluster(h, B, cl, threads);
-    if (cl) {
-        p.staged = cluster_smem_bytes(cl, p.N, p.max_out) <= PROP_SMEM_LIMIT ? 1 : 0;
+    {
+        // (a presorted launch never looks at the scores' order: no staged keys)
+        p.staged = (!p.presorted && cluster_smem_bytes(cl, p.N, p.max_out) <= PROP_SMEM_LIMIT) ? 1 : 0;
         const size_t smem = cluster_smem_bytes(cl, p.staged ? p.N : 0, p.max_out);
         if (smem > PROP_SMEM_LIMIT)
             return fail(TFRPN_ERR_UNSUPPORTED, "NMS: %d output rows need %zu B of shared memory (> %zu)", p.max_out, smem,
@@ -1446,6 +1479,13 @@ static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
         TFRPN_AFTER_LAUNCH("proposal_cluster_kernel");
         return 0;
     }
+}
+
+static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
+    p.mo_pad = (p.max_out + 3) & ~3;
+    int cl = 0, threads = 1024;
+    pick_cluster(h, B, cl, threads);
+    if (cl) return launch_cluster(h, p, B, cl, threads, st);
     p.staged = prop_smem_bytes(p.N, p.max_out) <= PROP_SMEM_LIMIT ? 1 : 0;
     const size_t smem = prop_smem_bytes(p.staged ? p.N : 0, p.max_out);
     if (smem > PROP_SMEM_LIMIT)
@@ -1533,14 +1573,9 @@ extern "C" int tfrpn_nms(tfrpn_handle h, const float* boxes, const float* scores
 }
 
 namespace tfrpn {
-// The fused stage after argument checks.  `rpn_reg` may also be PAGE-LOCKED HOST memory (pipeline.cu): the kernels
-// touch only the rows of the candidates they examine (<= ~1000 of the N rows per image), so those rows are
-// pulled over PCIe by the loads themselves instead of copying the whole tensor to the device first.
-int proposals_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B, int N,
-                      const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
-                      int32_t* keep_idx_or_null, unsigned long long* rows_fetched_or_null, cudaStream_t st) {
-    PropParams p = {};
-    p.rows_fetched = rows_fetched_or_null;
+static void fill_proposal_params(PropParams& p, const float* rpn_reg, const float* rpn_cls, const float* anchors, int N,
+                                 const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
+                                 int32_t* keep_idx_or_null) {
     p.mode = MODE_PROPOSALS; p.N = N; p.k = min(cfg->pre_nms_topn, N); p.scores = rpn_cls; p.use_sthr = 0;
     p.reg = reinterpret_cast<const float4*>(rpn_reg); p.anchors = reinterpret_cast<const float4*>(anchors);
     p.var = make_float4(cfg->variances[0], cfg->variances[1], cfg->variances[2], cfg->variances[3]);
@@ -1549,6 +1584,78 @@ int proposals_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls
     p.iou_thr = make_threshold(cfg->nms_iou_threshold); p.clip_out = 1;  // combined NMS default clip_boxes=True
     p.out_boxes = reinterpret_cast<float4*>(out_boxes); p.out_scores = out_scores; p.out_classes = nullptr;
     p.valid = valid; p.keep_idx = keep_idx_or_null;
+}
+
+// ---- two-phase flow of the host pipeline (pipeline.cu) ------------------------------------------------------
+// A host step's rpn_reg tensor is 80 % of its H2D bytes, and NMS decodes only the rows of the candidates it
+// examines (~550 of 8649 per image at C2).  So: (1) rank launch over the scores alone -> the entry index of the
+// first batch of ranks (<= 1024 per image, sorted); (2) the host gathers those rows of rpn_reg into a compact
+// array and copies it; (3) presorted launch = the NMS rounds of that batch, rows read by rank.  An image whose
+// NMS needs more than that batch raises redo_flags[b] and is redone by the unfiltered kernel (proposals_redo).
+constexpr int RANK_CAP = BATCH;
+int proposals_rank_cap() { return RANK_CAP; }
+bool proposals_two_phase_applies(int B, int N, const tfrpn_proposal_cfg* cfg) {
+    const int k = min(cfg->pre_nms_topn, N);
+    int k_eff = k;
+    if (cfg->post_nms_topn <= PRE_NMS_CAP_MAX_OUT) k_eff = min(k, PRE_NMS_CAP);
+    if (pre_applies(N, k_eff)) return false;                           // large N: the prefilter path
+    return B > 0 && cluster_smem_bytes(2, 0, cfg->post_nms_topn) <= PROP_SMEM_LIMIT;
+}
+static void two_phase_shape(tfrpn_handle h, int B, int& cl, int& threads) {
+    pick_cluster(h, B, cl, threads);
+    if (cl == 0) { cl = 2; threads = 512; }                            // the one-CTA kernel has no rank / presorted modes
+}
+int proposals_rank_enqueue(tfrpn_handle h, const float* rpn_cls, int B, int N, const tfrpn_proposal_cfg* cfg,
+                           int32_t* rank_idx, int32_t* rank_n, int32_t* rank_more, cudaStream_t st) {
+    PropParams p = {};
+    fill_proposal_params(p, nullptr, rpn_cls, nullptr, N, cfg, nullptr, nullptr, nullptr, nullptr);
+    p.mode = MODE_RANK;
+    p.rank_idx = rank_idx; p.rank_n = rank_n; p.rank_more = rank_more;
+    int cl, threads;
+    two_phase_shape(h, B, cl, threads);
+    return launch_cluster(h, p, B, cl, threads, st);
+}
+// reg_compact: (B, compact_stride, 4) rows of rpn_reg in rank order, the first compact_rows of every image valid;
+// ranks beyond them end the batch (and raise the image's redo flag if max_out boxes were not kept by then).
+// reg_compact null: rows are read from rpn_reg_or_null by entry index (device-resident two-phase run, tests).
+int proposals_presorted_enqueue(tfrpn_handle h, const float* rpn_reg_or_null, const float* reg_compact, int compact_rows,
+                                int compact_stride, const float* rpn_cls, const float* anchors, int B, int N,
+                                const tfrpn_proposal_cfg* cfg, int32_t* rank_idx, int32_t* rank_n, int32_t* rank_more,
+                                float* out_boxes, float* out_scores, int32_t* valid, int32_t* keep_idx_or_null,
+                                int32_t* redo_flags, unsigned long long* rows_fetched_or_null, cudaStream_t st) {
+    PropParams p = {};
+    fill_proposal_params(p, rpn_reg_or_null, rpn_cls, anchors, N, cfg, out_boxes, out_scores, valid, keep_idx_or_null);
+    p.rows_fetched = rows_fetched_or_null;
+    p.presorted = 1;
+    p.rank_idx = rank_idx; p.rank_n = rank_n; p.rank_more = rank_more;
+    p.reg_compact = reinterpret_cast<const float4*>(reg_compact); p.compact_rows = reg_compact ? compact_rows : 0;
+    p.compact_stride = compact_stride;
+    p.redo_flags = redo_flags;
+    int cl, threads;
+    two_phase_shape(h, B, cl, threads);
+    return launch_cluster(h, p, B, cl, threads, st);
+}
+// the unfiltered kernel for the images whose redo flag is set (it returns at once for the others)
+int proposals_redo_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B, int N,
+                           const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
+                           int32_t* keep_idx_or_null, const int32_t* redo_flags, unsigned long long* rows_fetched_or_null,
+                           cudaStream_t st) {
+    PropParams p = {};
+    fill_proposal_params(p, rpn_reg, rpn_cls, anchors, N, cfg, out_boxes, out_scores, valid, keep_idx_or_null);
+    p.rows_fetched = rows_fetched_or_null;
+    p.flags = redo_flags; p.flag_mode = 2;
+    return launch_one(h, p, B, st);
+}
+
+// The fused stage after argument checks.  `rpn_reg` may also be PAGE-LOCKED HOST memory (pipeline.cu): the kernels
+// touch only the rows of the candidates they examine (<= ~1000 of the N rows per image), so those rows are
+// pulled over PCIe by the loads themselves instead of copying the whole tensor to the device first.
+int proposals_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B, int N,
+                      const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
+                      int32_t* keep_idx_or_null, unsigned long long* rows_fetched_or_null, cudaStream_t st) {
+    PropParams p = {};
+    fill_proposal_params(p, rpn_reg, rpn_cls, anchors, N, cfg, out_boxes, out_scores, valid, keep_idx_or_null);
+    p.rows_fetched = rows_fetched_or_null;
     return launch(h, p, B, st);
 }
 }  // namespace tfrpn

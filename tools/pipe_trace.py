@@ -25,9 +25,9 @@ for i in range(DEPTH):
 pipe.drain()
 rows = []
 def trace(t):
-    ms = (C.c_float * 8)()
+    ms = (C.c_float * 10)()
     _lib.check(lib.tfrpn_pipeline_trace(pipe._pipe, t, ms))
-    rows.append((t, [1e3 * x for x in ms]))
+    rows.append((t, [1e3 * x for x in ms]))   # us
 tk = []
 n = 40
 for i in range(n):
@@ -42,8 +42,8 @@ t0 = rows[0][1][0]
 print("depth %d mode %s; us since step %d's H2D began" % (DEPTH, mode, rows[0][0]))
 print("%6s | %15s | %15s | %15s | %15s" % ("step", "H2D", "targets", "proposals", "D2H"))
 for t, m in rows:
-    m = [x - t0 for x in m]
-    print("%6d | %7.1f %7.1f | %7.1f %7.1f | %7.1f %7.1f | %7.1f %7.1f" % (t, *m))
+    m = [x - t0 for x in m[:8]] + m[8:]
+    print("%6d | %7.1f %7.1f | %7.1f %7.1f | %7.1f %7.1f | %7.1f %7.1f | gather %6.1f expand %6.1f" % (t, *m))
 d = np.array([m for _, m in rows])
 print("durations us (median): H2D %.1f targets %.1f proposals %.1f D2H %.1f | step period %.1f"
-      % tuple(np.median(d[:, 2 * k + 1] - d[:, 2 * k]) for k in range(4)) + (np.median(np.diff(d[:, 7])),))
+      % (tuple(np.median(d[:, 2 * k + 1] - d[:, 2 * k]) for k in range(4)) + (np.median(np.diff(d[:, 7])),)))
