@@ -107,6 +107,15 @@ def test_acquired_few_gathered_rows_redone_on_device(cuda_device):
     assert copied[-1][0] > 6 * 8649 * 4 + 6 * 128 * 16     # scores + gathered rows + pulled rows
 
 
+def test_acquired_device_side_gather(cuda_device):
+    """TFRPN_PIPE_GATHER=device: a kernel reads the candidate rows from the page-locked tensor (no host stage);
+    with few rows per image the flagged images are redone as well"""
+    copied = run_acquired(cuda_device, 64, 50, 4, 6, {"TFRPN_PIPE_GATHER": "device"})
+    assert copied[-1][0] < 0.4 * (64 * 8649 * 20 + 64 * 50 * 20)
+    run_acquired(cuda_device, 5, 9, 3, 4, {"TFRPN_PIPE_GATHER": "device", "TFRPN_PIPE_GATHER_ROWS": 200})
+    run_acquired(cuda_device, 5, 9, 3, 4, {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": 2})
+
+
 def test_acquired_dense_input_switch_equals_two_phase(cuda_device):
     run_acquired(cuda_device, 7, 5, 3, 4, {"TFRPN_PIPE_DENSE_IN": 1})
     run_acquired(cuda_device, 7, 5, 3, 4, {"TFRPN_PIPE_DENSE": 1})

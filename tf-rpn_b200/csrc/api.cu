@@ -181,6 +181,7 @@ extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
     h->opts.pipe_trace = getenv("TFRPN_PIPE_TRACE") != nullptr;
     h->opts.pipe_gather_rows = env_int("TFRPN_PIPE_GATHER_ROWS", 0);
     h->opts.host_threads = env_int("TFRPN_HOST_THREADS", 0);
+    if (const char* g = getenv("TFRPN_PIPE_GATHER")) h->opts.pipe_gather = !strcmp(g, "host") ? 1 : (!strcmp(g, "device") ? 2 : 0);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     // device counter of the loss reduction (losses.cu): zero between calls, the kernel resets it
     if (cudaMalloc(&h->ticket, 256) != cudaSuccess || cudaMemset(h->ticket, 0, 256) != cudaSuccess) {

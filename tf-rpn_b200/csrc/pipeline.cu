@@ -28,6 +28,7 @@
 //                         the whole tensor, which is why the host gathers.
 //   compact bbox_deltas   exactly zero outside the <= total_pos sampled positives (train_utils.py:137):
 //                         only those rows come back and a host function scatters them into the dense array.
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -65,6 +66,8 @@ int proposals_redo_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rp
                            const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
                            int32_t* keep_idx_or_null, const int32_t* redo_flags, unsigned long long* rows_fetched_or_null,
                            cudaStream_t st);
+int proposals_gather_enqueue(const float* reg_pinned_dev, const int32_t* rank_idx, const int32_t* rank_n, int B, int N,
+                             int rows, float* dst, int stride, unsigned long long* counter_or_null, cudaStream_t st);
 }
 
 namespace {
@@ -191,6 +194,7 @@ struct Layout {
 struct Step {
     bool do_t = false, do_p = false, acquired = false, compact = false, two_phase = false;
     bool reg_pinned = false;            // the caller's rpn_reg is page-locked: the device can read it (redo pulls rows)
+    bool device_gather = false;         // the rows are gathered by a kernel reading the page-locked tensor (no host stage)
     int B = 0, N = 0, G = 0, P = 0, GR = 0, total_pos = 0;
     Layout L = {};
     const float* anchors = nullptr;
@@ -259,6 +263,7 @@ struct tfrpn_pipe {
     long long last_pulled = 0;                        // bytes of rpn_reg rows gathered / pulled for the last RETIRED step
     int gather_rows = 640;                            // rows of rpn_reg per image the two-phase transfer sends (adapts)
     bool gather_adapt = true;
+    bool device_gather = false;                       // page-locked tensors: gather on the device instead of the host
 };
 
 namespace tfrpn {
@@ -382,13 +387,18 @@ static int enqueue_tail(tfrpn_pipe* p, Slot& s) {
         float* os = reinterpret_cast<float*>(d + L.os);
         int32_t* v = reinterpret_cast<int32_t*>(d + L.v);
         int32_t* k = reinterpret_cast<int32_t*>(d + L.k);
-        TFRPN_CHECK_CUDA(cudaMemcpyAsync(d + L.rc, pin + L.rc, (size_t)B * GR * 16, cudaMemcpyHostToDevice, s.s_prop));
+        unsigned long long* pc = reinterpret_cast<unsigned long long*>(d + L.pc);   // (zeroed by pipe_submit)
+        if (st.device_gather) {
+            if (int rc = proposals_gather_enqueue(st.reg_dev, ri, rn, B, N, GR, reinterpret_cast<float*>(d + L.rc), GR, pc, s.s_prop))
+                return rc;
+        } else {
+            TFRPN_CHECK_CUDA(cudaMemcpyAsync(d + L.rc, pin + L.rc, (size_t)B * GR * 16, cudaMemcpyHostToDevice, s.s_prop));
+        }
         if (int rc = proposals_presorted_enqueue(h, nullptr, reinterpret_cast<const float*>(d + L.rc), GR, GR, cls, st.anchors,
                                                  B, N, &st.pcfg, ri, rn, rm, ob, os, v, k, rf, nullptr, s.s_prop)) return rc;
         // images whose NMS ran out of gathered rows (rare): the unfiltered kernel redoes them, reading the rows it
         // needs straight from the caller's page-locked tensor; a pageable tensor is handled when the step is retired
         if (st.reg_pinned) {
-            unsigned long long* pc = reinterpret_cast<unsigned long long*>(d + L.pc);   // (zeroed by pipe_submit)
             if (int rc = proposals_redo_enqueue(h, st.reg_dev, cls, st.anchors, B, N, &st.pcfg, ob, os, v, k, rf, pc, s.s_prop))
                 return rc;
         }
@@ -501,10 +511,19 @@ static int pipe_create(tfrpn_handle h, int depth, tfrpn_pipe** out) {
     p->h = h;
     p->depth = depth;
     int threads = h->opts.host_threads;
-    if (threads <= 0) {   // default: half of the cores, at most 8 (the other ranks of a multi-GPU job and the data loader need theirs)
-        const int hw = (int)std::thread::hardware_concurrency();
-        threads = hw / 2 < 1 ? 1 : (hw / 2 > 8 ? 8 : hw / 2);
+    if (threads <= 0) {
+        // default: half of this process's share of the cores it may run on, at most 8 -- the data loader and the
+        // other ranks of a multi-GPU job (torchrun exports LOCAL_WORLD_SIZE) need theirs
+        int hw = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = CPU_COUNT(&set);
+        const char* lws = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lws && atoi(lws) > 0 ? atoi(lws) : 1;
+        const int share = hw / ranks;
+        threads = share / 2 < 1 ? 1 : (share / 2 > 8 ? 8 : share / 2);
     }
+    // TFRPN_PIPE_GATHER = host | device (default: host when the pool has >= 4 threads, else device)
+    p->device_gather = h->opts.pipe_gather == 2 || (h->opts.pipe_gather == 0 && threads < 4);
     if (depth == 1) threads = threads > 2 ? 2 : threads;   // a synchronous step only uses the pool for staging copies
     p->pool.reset(new HostPool(threads > 16 ? 16 : threads));
     p->gather_rows = initial_gather_rows(h);
@@ -694,10 +713,12 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         cudaGetLastError();
         st.reg_dev = st.reg_pinned ? static_cast<const float*>(attr.devicePointer) : nullptr;
     }
+    // who gathers: host threads when the pool has enough of them (lower latency, one bulk copy), else the device
+    st.device_gather = two_phase && st.reg_pinned && p->device_gather;
     s.pulled = two_phase && st.reg_pinned;
     s.gathered = 0;
     s.svc_rc = 0;
-    s.svc_pending.store(two_phase ? 1 : 0, std::memory_order_release);
+    s.svc_pending.store(two_phase && !st.device_gather ? 1 : 0, std::memory_order_release);
 
     p->last_h2d = p->last_d2h = 0;
     if (acquired) {
@@ -726,11 +747,13 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         if (int rc = proposals_rank_enqueue(h, reinterpret_cast<const float*>(d + L.cls), B, N, a.pcfg,
                                             reinterpret_cast<int32_t*>(d + L.ri), reinterpret_cast<int32_t*>(d + L.rn),
                                             reinterpret_cast<int32_t*>(d + L.rm), s.s_prop)) return rc;
-        TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin + L.ri, d + L.ri, L.rank_end - L.ri, cudaMemcpyDeviceToHost, s.s_prop));
-        TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_rank, s.s_prop));
-        if (st.reg_pinned) TFRPN_CHECK_CUDA(cudaMemsetAsync(d + L.pc, 0, 8, s.s_prop));   // rows the redo launch pulls
-        p->last_h2d += (long long)B * GR * 16;
-        p->last_d2h += (long long)(L.rank_end - L.ri);
+        if (st.reg_pinned) TFRPN_CHECK_CUDA(cudaMemsetAsync(d + L.pc, 0, 8, s.s_prop));   // rows the device pulls itself
+        if (!st.device_gather) {
+            TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin + L.ri, d + L.ri, L.rank_end - L.ri, cudaMemcpyDeviceToHost, s.s_prop));
+            TFRPN_CHECK_CUDA(cudaEventRecord(s.ev_rank, s.s_prop));
+            p->last_h2d += (long long)B * GR * 16;
+            p->last_d2h += (long long)(L.rank_end - L.ri);
+        }
     }
     for (int c = 0; c < chunks; ++c) {
         const int lo = (int)((long long)B * c / chunks), hi = (int)((long long)B * (c + 1) / chunks), nb = hi - lo;
@@ -787,7 +810,7 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     }
     s.ticket = p->next_ticket++;
     if (ticket_out) *ticket_out = s.ticket;
-    if (two_phase) svc_push(p, STAGE_GATHER, &s);         // ... which ends by calling enqueue_tail
+    if (two_phase && !st.device_gather) svc_push(p, STAGE_GATHER, &s);   // ... which ends by calling enqueue_tail
     else if (int rc = enqueue_tail(p, s)) return rc;
     return 0;
 }

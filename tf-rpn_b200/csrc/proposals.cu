@@ -1481,6 +1481,29 @@ static int launch_cluster(tfrpn_handle h, PropParams& p, int B, int cl, int thre
     }
 }
 
+// Device-side variant of the two-phase gather (pipeline.cu): the candidate rows of a PAGE-LOCKED host tensor, in rank
+// order, into a compact device array.  Every row is an independent 16-byte read over PCIe (~0.55 G rows/s,
+// tools/src/pcie_gather.cu): slower than the host-side gather + one bulk copy when host cores are free, but it
+// costs no host time at all.  Lane pairs read the two halves of the row's 32-byte sector (one request per pair).
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restrict__ reg, const int* __restrict__ rank_idx,
+                                                          const int* __restrict__ rank_n, int N, int rows, int cap,
+                                                          float4* __restrict__ dst, int stride, unsigned long long* counter) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = t >> 1, half = t & 1;
+    const int n = min(rank_n[b], rows);
+    const bool live = r < n;
+    const int i = live ? rank_idx[(long long)b * cap + r] : 0;
+    const bool pair_ok = ((i & ~1) + 1) < N || (i & 1);      // the sector's other half exists (the last row of an odd N may not)
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* src = reg + (long long)b * N;
+    if (live) v = pair_ok ? __ldg(src + (i & ~1) + half) : (half == 0 ? __ldg(src + i) : v);
+    const float4 o = make_float4(__shfl_xor_sync(0xffffffffu, v.x, 1), __shfl_xor_sync(0xffffffffu, v.y, 1),
+                                 __shfl_xor_sync(0xffffffffu, v.z, 1), __shfl_xor_sync(0xffffffffu, v.w, 1));
+    if (live && half == 0) dst[(long long)b * stride + r] = (pair_ok && (i & 1)) ? o : v;
+    if (counter && t == 0) atomicAdd(counter, (unsigned long long)n);
+}
+
 static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
     p.mo_pad = (p.max_out + 3) & ~3;
     int cl = 0, threads = 1024;
@@ -1634,6 +1657,14 @@ int proposals_presorted_enqueue(tfrpn_handle h, const float* rpn_reg_or_null, co
     int cl, threads;
     two_phase_shape(h, B, cl, threads);
     return launch_cluster(h, p, B, cl, threads, st);
+}
+int proposals_gather_enqueue(const float* reg_pinned_dev, const int32_t* rank_idx, const int32_t* rank_n, int B, int N,
+                             int rows, float* dst, int stride, unsigned long long* counter_or_null, cudaStream_t st) {
+    const dim3 grid((2 * rows + 255) / 256, B);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(reg_pinned_dev), rank_idx, rank_n, N, rows, RANK_CAP,
+                                             reinterpret_cast<float4*>(dst), stride, counter_or_null);
+    TFRPN_AFTER_LAUNCH("gather_rows_kernel");
+    return 0;
 }
 // the unfiltered kernel for the images whose redo flag is set (it returns at once for the others)
 int proposals_redo_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B, int N,

@@ -2,13 +2,14 @@
 Keras from trainer.py:48-49,64-69) and the predictor loop (predictor.py:48-60), over the C-ABI
 ``tfrpn_pipeline_*`` entry points.
 
-A step moves ~11 MB over PCIe each way at C2 while its kernels take ~0.1 ms, so several steps are kept
-in flight: the H2D copy of step i+1 runs under the D2H copy of step i.  ``acquire()`` hands out NumPy
-views of one slot's page-locked buffers -- the data loader writes the padded batch (and the head outputs)
-straight into them and reads the results from them, so a step is exactly one copy per direction.  The
-bbox_deltas tensor is sparse by construction (exactly 0 outside the <= 128 sampled positives per image), so
-only those rows come back (2.8 MB of results instead of 11.5 MB at C2) and the library scatters them into
-the dense view when the step is waited for.
+A dense step would move ~11 MB over PCIe each way at C2 while its kernels take ~0.1 ms, so several steps are
+kept in flight and the bytes are cut to ~3 MB each way (csrc/pipeline.cu): only the scores are copied in, the
+device ranks them, the library's host threads gather the ~640 candidate rows per image of ``rpn_reg`` and only
+those follow; ``bbox_deltas`` is sparse by construction (exactly 0 outside the <= 128 sampled positives per
+image), so only those rows come back and the library scatters them into the dense array when the step is
+waited for.  ``acquire()`` hands out NumPy views of one slot's page-locked buffers -- the data loader writes the
+padded batch (and the head outputs) straight into them and reads the results from them; ``submit_arrays()``
+takes the caller's own (pageable) arrays instead.
 """
 import collections
 import ctypes as C
@@ -75,6 +76,7 @@ class HostPipeline:
         _lib.check(self._lib.tfrpn_pipeline_create(self._h, self.depth, C.byref(pipe)))
         self._pipe = pipe
         self._views = {}
+        self._keep = {}
 
     def acquire(self, batch, max_gt):
         B, G, N, P = int(batch), int(max_gt), self.N, self.P
@@ -103,6 +105,48 @@ class HostPipeline:
             self._pipe, self.anchors.data_ptr(), C.byref(tcfg) if targets else None,
             C.byref(self.pcfg) if proposals else None, C.byref(t)))
         return t.value
+
+    def submit_arrays(self, gt_boxes=None, gt_labels=None, rpn_reg=None, rpn_cls=None, out=None, seed=None, offset=None,
+                      image_offset=0):
+        """One step on the caller's own host arrays (``tfrpn_pipeline_submit``): NumPy arrays as the reference's
+        generator / predictor hold them (utils/train_utils.py:78-82, predictor.py:50), pageable or page-locked.
+        Nothing is copied by the caller: the library stages the small inputs, gathers the candidate rows of
+        ``rpn_reg`` in place and writes the results into ``out`` (allocated here unless given).  The arrays must
+        stay alive and unchanged until ``wait(ticket)``.  Returns ``(ticket, out)`` with ``out`` a dict of
+        bbox_deltas (B,N,4), bbox_labels (B,N), boxes (B,P,4), scores (B,P), valid (B,), keep_idx (B,P)."""
+        do_t, do_p = gt_boxes is not None, rpn_reg is not None
+        f32, i32 = np.float32, np.int32
+        if do_t:
+            gt_boxes = np.ascontiguousarray(gt_boxes, f32)
+            gt_labels = np.ascontiguousarray(gt_labels, i32)
+            B, G = gt_labels.shape
+        if do_p:
+            rpn_reg = np.ascontiguousarray(rpn_reg, f32)
+            rpn_cls = np.ascontiguousarray(rpn_cls, f32)
+            B = rpn_reg.shape[0]
+        N, P = self.N, self.P
+        if out is None:
+            out = {}
+        want = ([("bbox_deltas", (B, N, 4), f32), ("bbox_labels", (B, N), f32)] if do_t else []) + \
+               ([("boxes", (B, P, 4), f32), ("scores", (B, P), f32), ("valid", (B,), i32), ("keep_idx", (B, P), i32)] if do_p else [])
+        for name, shape, dt in want:
+            a = out.get(name)
+            if a is None:
+                out[name] = np.empty(shape, dt)
+            elif a.shape != shape or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("out[%r] must be a C-contiguous %s array of shape %s" % (name, np.dtype(dt).name, shape))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        tcfg = train_utils._target_cfg(self.hp, seed, offset, image_offset) if do_t else _lib.TargetCfg()
+        t = C.c_int64()
+        _lib.check(self._lib.tfrpn_pipeline_submit(
+            self._pipe, self.anchors.data_ptr(), B, N,
+            vp(gt_boxes) if do_t else None, vp(gt_labels) if do_t else None, G if do_t else 0, C.byref(tcfg),
+            vp(out["bbox_deltas"]) if do_t else None, vp(out["bbox_labels"]) if do_t else None,
+            vp(rpn_reg) if do_p else None, vp(rpn_cls) if do_p else None, C.byref(self.pcfg),
+            vp(out["boxes"]) if do_p else None, vp(out["scores"]) if do_p else None, vp(out["valid"]) if do_p else None,
+            vp(out["keep_idx"]) if do_p else None, C.byref(t)))
+        self._keep[t.value % max(self.depth, 1)] = (gt_boxes, gt_labels, rpn_reg, rpn_cls, out)   # alive until the slot is reused
+        return t.value, out
 
     def wait(self, ticket):
         _lib.check(self._lib.tfrpn_pipeline_wait(self._pipe, int(ticket)))
