@@ -476,12 +476,38 @@ def run_ours(args):
                     "frac": None, "traffic": traffic.get(dominant), "us_per_launch": dom_us, "peak_source": peak_src}
     if dominant.startswith("proposal") or dominant == "rpn_label_encode_kernel":
         # these kernels are bound by work (select / sort / greedy NMS per image), not by HBM: the
-        # HBM figures above are kept for the contract, the binding roof is instruction issue
+        # HBM figures above are kept for the contract, the binding roof is instruction issue on the SMs the
+        # launch occupies (one CTA, or one cluster of CTAs, per image)
         roofline["note"] = ("not HBM-bound: per-image select / sort / sequential greedy NMS; see `work` for the "
                             "issue-capacity view (warp instructions from the committed ncu capture)")
-        work = {"us_per_image_batch": dom_us, "images": B, "us_per_image": dom_us / B}
+        cl = 1 if dominant != "proposal_cluster_kernel" else (8 if B <= 32 else 2)     # proposals.cu: pick_cluster
+        sms_used = min(148, B * cl)
+        work = {"us_per_image_batch": dom_us, "images": B, "us_per_image": dom_us / B, "ctas": B * cl, "sms_used": sms_used}
+        if dominant.startswith("proposal") and rpn:
+            # NMS work actually scheduled: every round tests its <= 128 candidates against the kept list so far and
+            # against each other (sizes from the launch's own results: rank of every kept box)
+            s0 = sets[0]
+            proposals(s0, cur_s)
+            torch.cuda.synchronize()
+            keep, valid = s0["pk"].cpu().numpy(), s0["pv"].cpu().numpy()
+            sc = s0["cls"].reshape(B, -1).cpu().numpy()
+            order = np.argsort(-sc, axis=1, kind="stable")
+            rk = np.empty_like(order)
+            np.put_along_axis(rk, order, np.arange(N)[None, :].repeat(B, 0), axis=1)
+            pairs, examined = 0, []
+            for b_ in range(B):
+                kr = np.sort(rk[b_][keep[b_][:valid[b_]]])
+                last = int(kr[-1]) + 1 if len(kr) else 0
+                examined.append(last)
+                for lo_ in range(0, last, 128):   # a round tests all of its 128 candidates before it is resolved
+                    c_ = min(128, min(N, PRE_NMS) - lo_)
+                    pairs += c_ * int(np.searchsorted(kr, lo_)) + c_ * (c_ - 1) // 2
+            work.update({"pair_tests_per_launch": int(pairs), "pair_tests_per_s": pairs / (dom_us * 1e-6),
+                         "candidates_examined_per_image": float(np.mean(examined))})
         if dominant in winstr:
+            floor_us = winstr[dominant] / (sms_used * 4 * 1.965e9) * 1e6
             work.update({"bound": "issue", "warp_instr_per_launch": winstr[dominant],
+                         "issue_floor_us_on_sms_used": floor_us, "frac_issue_on_sms_used": floor_us / dom_us,
                          "achieved_gwarp_instr_per_s": winstr[dominant] / (dom_us * 1e-6) / 1e9,
                          "peak_gwarp_instr_per_s": issue_peak / 1e9, "frac": winstr[dominant] / (dom_us * 1e-6) / issue_peak})
         roofline["work"] = work

@@ -111,7 +111,7 @@ TFRPN_API uint64_t tfrpn_launch_count(void);
 /* ---- tracing (the reference has none): when enabled, every kernel launched through
  *      this handle is bracketed by CUDA events on its stream.  Not usable during graph capture. */
 enum { TFRPN_K_IOU_ARGMAX = 0, TFRPN_K_LABEL_ENCODE = 1, TFRPN_K_SELECT_MASK = 2, TFRPN_K_PROPOSAL = 3,
-       TFRPN_K_LOSS = 4, TFRPN_K_COUNT = 5 };
+       TFRPN_K_LOSS = 4, TFRPN_K_PROPOSAL_CLUSTER = 5, TFRPN_K_COUNT = 6 };
 TFRPN_API int tfrpn_profile_enable(tfrpn_handle h, int on);
 /* synchronises, then returns the summed device time and launch count of one kernel id and clears them */
 TFRPN_API int tfrpn_profile_read(tfrpn_handle h, int kernel_id, double* total_ms, int* launches);
@@ -142,6 +142,12 @@ TFRPN_API int tfrpn_encode_deltas(const float* boxes /* (N,4) or (B,N,4) */, int
 TFRPN_API int tfrpn_decode(const float* anchors /* (N,4) or (B,N,4) */, int anchors_batched,
                  const float* deltas /* (B,N,4) */, const float* variances_host_or_null /* [4] */,
                  int clip, int B, int N, float* out /* (B,N,4) */, tfrpn_stream s);
+
+/* The same with the anchors regenerated in registers from the hyper-parameters (utils/bbox_utils.py:23-46 fused
+ * in front of :72-96): no anchor tensor is read.  N = fm_h * fm_w * n_scales * n_ratios; out is (B,N,4). */
+TFRPN_API int tfrpn_decode_anchor_cfg(const tfrpn_anchor_cfg* acfg, const float* deltas /* (B,N,4) */,
+                            const float* variances_host_or_null /* [4] */, int clip, int B,
+                            float* out /* (B,N,4) */, tfrpn_stream s);
 
 /* ---- normalize_bboxes / denormalize_bboxes: utils/bbox_utils.py:152-182 ------------ */
 TFRPN_API int tfrpn_scale_boxes(const float* boxes, int64_t n_boxes, float height, float width,
@@ -235,6 +241,14 @@ TFRPN_API int tfrpn_proposals(tfrpn_handle h, const float* rpn_reg /* (B,N,4) ==
                     float* out_boxes /* (B,post,4) */, float* out_scores /* (B,post) */,
                     int32_t* valid /* (B,) */, int32_t* keep_idx_or_null /* (B,post) */,
                     tfrpn_stream s);
+
+/* ... with the anchors regenerated in registers (generate_anchors, utils/bbox_utils.py:23-46, fused into the
+ * decode of the candidates NMS examines).  N = fm_h * fm_w * n_scales * n_ratios, below the large-N prefilter's
+ * threshold (40000); larger feature maps use tfrpn_anchors + tfrpn_proposals. */
+TFRPN_API int tfrpn_proposals_anchor_cfg(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls,
+                               const tfrpn_anchor_cfg* acfg, int B, const tfrpn_proposal_cfg* cfg,
+                               float* out_boxes, float* out_scores, int32_t* valid, int32_t* keep_idx_or_null,
+                               tfrpn_stream s);
 
 /* ---- host-buffer entry points (what a NumPy / tf.numpy() caller binds): pinned staging,
  *      H2D, kernels, D2H, stream sync -- all inside the call ---------------------------- */

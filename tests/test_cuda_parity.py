@@ -917,3 +917,36 @@ def test_iou_map_nice_and_fallback_paths_agree_with_oracle(T):
     gt52[3, 1] = [0.5, 0.5, 0.2, 0.2]
     gt52[0, 2] = [1e-7, 0.1, 0.3, 0.4]
     assert bits_equal(T.np(T.bbox.generate_iou_map(T.cu(anchors), T.cu(gt52))), O.generate_iou_map(anchors, gt52))
+
+
+# ---------------------------------------------------------------- anchors regenerated in registers (north star bullet 1)
+@pytest.mark.parametrize("hp", [O.get_hyper_params("vgg16"), O.get_hyper_params("mobilenet_v2"), HP_C4],
+                         ids=["vgg16", "mobilenet_v2", "c4_1333x800"])
+def test_decode_with_regenerated_anchors_equals_anchor_tensor(T, hp):
+    """tfrpn_decode_anchor_cfg (generate_anchors fused into the decode) == tfrpn_decode on the anchor tensor, bit for bit"""
+    anchors = T.bbox.generate_anchors(hp)
+    N = anchors.shape[0]
+    rng = np.random.default_rng(17)
+    deltas = T.cu(rng.normal(0, 0.5, size=(3, N, 4)).astype(F32))
+    for var, clip in ((None, False), (hp["variances"], True)):
+        want = T.bbox.get_bboxes_from_deltas(anchors, deltas * T.cu(np.asarray(var, F32)) if var is not None else deltas)
+        if clip:
+            want = want.clamp(0, 1)
+        got = T.bbox.get_bboxes_from_hyper_params(hp, deltas, variances=var, clip=clip)
+        assert T.torch.equal(got, want)
+
+
+@pytest.mark.parametrize("cfg,B", [("C1", 1), ("C2", 64), ("C3", 16), ("C4", 3)])
+def test_proposals_with_regenerated_anchors_equal_anchor_tensor(T, cfg, B):
+    """tfrpn_proposals_anchor_cfg == tfrpn_proposals with the anchor tensor (and hence the oracle), bit for bit"""
+    from tfrpn import synthetic
+    bb, _, G, over = synthetic.CONFIGS[cfg]
+    hp = dict(O.get_hyper_params(bb), **over)
+    fm = hp["feature_map_shape"]
+    fm_h, fm_w = (fm, fm) if isinstance(fm, int) else fm
+    anchors = T.bbox.generate_anchors(hp)
+    reg, cls = synthetic.head_outputs(np.random.default_rng(77), B, fm_h, fm_w, 9)
+    a = T.tfrpn.generate_proposals(T.cu(reg), T.cu(cls), anchors, hp, pre_nms_topn=6000)
+    b = T.tfrpn.generate_proposals(T.cu(reg), T.cu(cls), None, hp, pre_nms_topn=6000)
+    for x, y in zip(a, b):
+        assert T.torch.equal(x, y)

@@ -152,6 +152,7 @@ extern "C" const char* tfrpn_kernel_name(int id) {
         case TFRPN_K_LABEL_ENCODE: return "rpn_label_encode_kernel";
         case TFRPN_K_SELECT_MASK: return "select_mask_kernel";
         case TFRPN_K_PROPOSAL: return "proposal_kernel";
+        case TFRPN_K_PROPOSAL_CLUSTER: return "proposal_cluster_kernel";
         case TFRPN_K_LOSS: return "rpn_loss_partial_kernel";
         default: return "?";
     }
@@ -204,6 +205,7 @@ extern "C" int tfrpn_destroy(tfrpn_handle h) {
     if (h->pinned2) cudaFreeHost(h->pinned2);
     if (h->step_pipe) pipe_destroy(h->step_pipe);
     if (h->ticket) cudaFree(h->ticket);
+    if (h->anchor_gen) cudaFree(h->anchor_gen);
     delete h;
     return 0;
 }

@@ -2,6 +2,7 @@
 // Replaces utils/bbox_utils.py:3-46, :72-96, :98-124, :126-150, :152-182 of the reference.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -11,23 +12,10 @@ namespace tfrpn {
 // K0 anchors (utils/bbox_utils.py:23-46).  One thread per anchor; the grid coordinate is evaluated
 // in float64 exactly like `tf.range(0,F)/F + stride/2` (int32 truediv -> f64) and rounded once.
 // ------------------------------------------------------------------------------------------------
-struct BaseAnchors {
-    float4 box[TFRPN_MAX_BASE_ANCHORS];
-};
-
-__global__ void __launch_bounds__(256) anchors_kernel(BaseAnchors base, int A, int fm_h, int fm_w,
-                                                      double half_stride_y, double half_stride_x,
-                                                      float4* __restrict__ out) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    int N = fm_h * fm_w * A;
-    if (n >= N) return;
-    int c = n / A, a = n - c * A;
-    int i = c / fm_w, j = c - i * fm_w;
-    float y = __double2float_rn(__dadd_rn(__ddiv_rn((double)i, (double)fm_h), half_stride_y));
-    float x = __double2float_rn(__dadd_rn(__ddiv_rn((double)j, (double)fm_w), half_stride_x));
-    float4 b = base.box[a];
-    float4 o = make_float4(__fadd_rn(b.x, y), __fadd_rn(b.y, x), __fadd_rn(b.z, y), __fadd_rn(b.w, x));
-    out[n] = clip01(o);
+__global__ void __launch_bounds__(256) anchors_kernel(const __grid_constant__ AnchorGen gen, float4* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= gen.fm_h * gen.fm_w * gen.A) return;
+    out[n] = anchor_at(gen, n);
 }
 
 static int check_anchor_cfg(const tfrpn_anchor_cfg* cfg) {
@@ -56,6 +44,21 @@ static int base_anchors_host(const tfrpn_anchor_cfg* cfg, float* out) {
             out[a * 4 + 3] = w / 2.0f;
         }
     }
+    return 0;
+}
+
+int make_anchor_gen(const tfrpn_anchor_cfg* cfg, AnchorGen* out, long long* n_anchors) {
+    if (int rc = check_anchor_cfg(cfg)) return rc;
+    float tmp[TFRPN_MAX_BASE_ANCHORS * 4];
+    base_anchors_host(cfg, tmp);
+    const int A = cfg->n_scales * cfg->n_ratios;
+    memset(out, 0, sizeof(*out));
+    for (int a = 0; a < A; ++a) out->base[a] = make_float4(tmp[4 * a], tmp[4 * a + 1], tmp[4 * a + 2], tmp[4 * a + 3]);
+    out->A = A; out->fm_h = cfg->fm_h; out->fm_w = cfg->fm_w;
+    out->half_stride_y = (1.0 / cfg->fm_h) / 2; out->half_stride_x = (1.0 / cfg->fm_w) / 2;
+    const long long N = (long long)cfg->fm_h * cfg->fm_w * A;
+    if (N > (1LL << 30)) return fail(TFRPN_ERR_BAD_ARG, "too many anchors");
+    if (n_anchors) *n_anchors = N;
     return 0;
 }
 
@@ -286,6 +289,32 @@ __global__ void __launch_bounds__(EW_THREADS) decode_kernel(const float4* __rest
     }
 }
 
+// The north star's fused anchor-generate + decode + clip: the same kernel with the anchors regenerated in
+// registers (anchor_at) instead of read -- 32 instead of 48 bytes of requests per box (the (N,4) tensor is shared
+// by the batch and L2-resident, so the DRAM traffic is the same 32 B).
+template <bool SCALE, bool CLIP, int PT>
+__global__ void __launch_bounds__(EW_THREADS) decode_gen_kernel(const __grid_constant__ AnchorGen gen,
+                                                                const float4* __restrict__ deltas, float4 var, int N,
+                                                                float4* __restrict__ out) {
+    const long long img = (long long)blockIdx.y * N;
+    const int n0 = blockIdx.x * (EW_THREADS * PT) + threadIdx.x;
+    float4 d[PT];
+#pragma unroll
+    for (int u = 0; u < PT; ++u) {
+        const int n = n0 + u * EW_THREADS;
+        if (n < N) d[u] = ldg_f4_stream(deltas + img + n);
+    }
+#pragma unroll
+    for (int u = 0; u < PT; ++u) {
+        const int n = n0 + u * EW_THREADS;
+        if (n < N) {
+            float4 o = decode_ref(anchor_at(gen, n), SCALE ? mul4(d[u], var) : d[u]);
+            if (CLIP) o = clip01(o);
+            stg_f4_stream(out + img + n, o);
+        }
+    }
+}
+
 // normalize_bboxes / denormalize_bboxes (utils/bbox_utils.py:152-182)
 __global__ void __launch_bounds__(EW_THREADS) scale_boxes_kernel(const float4* __restrict__ in, long long total,
                                                                  float h, float w, int denorm,
@@ -394,17 +423,11 @@ extern "C" int tfrpn_anchors(const tfrpn_anchor_cfg* cfg, float* out, tfrpn_stre
     if (!out) return fail(TFRPN_ERR_BAD_ARG, "out is null");
     if (!aligned16(out)) return fail(TFRPN_ERR_MISALIGNED, "anchors output must be 16-byte aligned");
     TFRPN_ENTER_PTR(out, "anchors: out");
-    BaseAnchors base;
-    float tmp[TFRPN_MAX_BASE_ANCHORS * 4];
-    base_anchors_host(cfg, tmp);
-    int A = cfg->n_scales * cfg->n_ratios;
-    for (int a = 0; a < A; ++a) base.box[a] = make_float4(tmp[4 * a], tmp[4 * a + 1], tmp[4 * a + 2], tmp[4 * a + 3]);
-    long long N = (long long)cfg->fm_h * cfg->fm_w * A;
-    if (N > (1LL << 30)) return fail(TFRPN_ERR_BAD_ARG, "too many anchors");
-    double hy = (1.0 / cfg->fm_h) / 2, hx = (1.0 / cfg->fm_w) / 2;
+    AnchorGen gen;
+    long long N = 0;
+    if (int rc = make_anchor_gen(cfg, &gen, &N)) return rc;
     int blocks = (int)((N + 255) / 256);
-    anchors_kernel<<<blocks, 256, 0, as_stream(s)>>>(base, A, cfg->fm_h, cfg->fm_w, hy, hx,
-                                                     reinterpret_cast<float4*>(out));
+    anchors_kernel<<<blocks, 256, 0, as_stream(s)>>>(gen, reinterpret_cast<float4*>(out));
     TFRPN_AFTER_LAUNCH("anchors_kernel");
     return 0;
 }
@@ -484,6 +507,34 @@ extern "C" int tfrpn_decode(const float* anchors, int anchors_batched, const flo
     if (pt == 1) TFRPN_DECODE_LAUNCH(1); else if (pt == 4) TFRPN_DECODE_LAUNCH(4); else TFRPN_DECODE_LAUNCH(2);
 #undef TFRPN_DECODE_LAUNCH
     TFRPN_AFTER_LAUNCH("decode_kernel");
+    return 0;
+}
+
+extern "C" int tfrpn_decode_anchor_cfg(const tfrpn_anchor_cfg* acfg, const float* deltas, const float* variances_host_or_null,
+                                       int clip, int B, float* out, tfrpn_stream s) {
+    if (!deltas || !out) return fail(TFRPN_ERR_BAD_ARG, "decode_anchor_cfg: null pointer");
+    if (B < 0) return fail(TFRPN_ERR_BAD_ARG, "decode_anchor_cfg: negative shape");
+    AnchorGen gen;
+    long long N = 0;
+    if (int rc = make_anchor_gen(acfg, &gen, &N)) return rc;
+    if (B == 0) return 0;
+    if (!aligned16(deltas) || !aligned16(out)) return fail(TFRPN_ERR_MISALIGNED, "decode_anchor_cfg: pointers must be 16-byte aligned");
+    if (B > 65535) return fail(TFRPN_ERR_UNSUPPORTED, "decode_anchor_cfg: B > 65535");
+    float4 var = make_float4(1.f, 1.f, 1.f, 1.f);
+    const bool scale = variances_host_or_null != nullptr;
+    if (scale) var = make_float4(variances_host_or_null[0], variances_host_or_null[1], variances_host_or_null[2],
+                                 variances_host_or_null[3]);
+    TFRPN_ENTER_PTR(out, "decode_anchor_cfg: out");
+    const float4* d4 = reinterpret_cast<const float4*>(deltas);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    cudaStream_t st = as_stream(s);
+    constexpr int PT = 2;
+    const dim3 grid((unsigned)((N + EW_THREADS * PT - 1) / (EW_THREADS * PT)), B);
+    if (scale && clip) decode_gen_kernel<true, true, PT><<<grid, EW_THREADS, 0, st>>>(gen, d4, var, (int)N, o4);
+    else if (scale) decode_gen_kernel<true, false, PT><<<grid, EW_THREADS, 0, st>>>(gen, d4, var, (int)N, o4);
+    else if (clip) decode_gen_kernel<false, true, PT><<<grid, EW_THREADS, 0, st>>>(gen, d4, var, (int)N, o4);
+    else decode_gen_kernel<false, false, PT><<<grid, EW_THREADS, 0, st>>>(gen, d4, var, (int)N, o4);
+    TFRPN_AFTER_LAUNCH("decode_gen_kernel");
     return 0;
 }
 

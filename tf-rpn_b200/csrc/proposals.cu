@@ -66,6 +66,7 @@ struct PropParams {
     long long box_stride;  // elements between images (0 = shared (N,4))
     const float4* reg;     // MODE_PROPOSALS: (B,N,4) head regression output
     const float4* anchors; // MODE_PROPOSALS: (N,4)
+    const AnchorGen* gen;  //   ... or null `anchors` and the generator: anchors are regenerated in registers
     float4 var;
     int clip_decoded;
     float* values;   // MODE_TOPK (B,k)
@@ -109,6 +110,11 @@ struct PropShared {
     int nk;
     int nalive;
 };
+
+// anchor i of the image: read from the (N,4) tensor, or regenerated (utils/bbox_utils.py:23-46)
+__device__ __forceinline__ float4 anchor_of(const PropParams& p, const float4* anc, uint32_t i) {
+    return p.gen ? anchor_at(*p.gen, (int)i) : ldg_f4(anc + i);
+}
 
 // score -> sortable key; entries at or below the score threshold get key 0 (below every real key)
 __device__ __forceinline__ uint32_t score_key(float s, int use_sthr, float sthr) {
@@ -334,7 +340,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 p.indices[o] = remap ? remap[my_i] : (int)my_i;
                 if (p.gathered) {
                     if (p.reg) {   // predictor.py:55-56 for the selected rows only: decode(anchor, delta * variances)
-                        float4 bx = decode_ref(ldg_f4(anc + my_i), mul4(ldg_f4(p.reg + (long long)b * SN + my_i), p.var));
+                        float4 bx = decode_ref(anchor_of(p, anc, my_i), mul4(ldg_f4(p.reg + (long long)b * SN + my_i), p.var));
                         p.gathered[o] = p.clip_decoded ? clip01(bx) : bx;
                     } else {
                         p.gathered[o] = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 idx = sidx[pos + tid];
                 if (p.mode == MODE_PROPOSALS) {
                     d = ldg_f4(p.reg + (long long)b * SN + idx);
-                    a = ldg_f4(anc + idx);
+                    a = anchor_of(p, anc, idx);
                 } else {
                     a = ldg_f4(p.boxes + (long long)b * p.box_stride + idx);
                 }
@@ -897,7 +903,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
                 p.indices[o] = remap ? remap[my_i] : (int)my_i;
                 if (p.gathered) {
                     if (p.reg) {
-                        float4 bx = decode_ref(ldg_f4(anc + my_i), mul4(ldg_f4(p.reg + (long long)b * SN + my_i), p.var));
+                        float4 bx = decode_ref(anchor_of(p, anc, my_i), mul4(ldg_f4(p.reg + (long long)b * SN + my_i), p.var));
                         p.gathered[o] = p.clip_decoded ? clip01(bx) : bx;
                     } else {
                         p.gathered[o] = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
@@ -918,7 +924,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
                 const float4 row = (p.presorted && p.reg_compact && rank < p.compact_rows)
                                        ? ldg_f4(p.reg_compact + (long long)b * p.compact_stride + rank)
                                        : ldg_f4(p.reg + (long long)b * SN + my_i);
-                raw = decode_ref(ldg_f4(anc + my_i), mul4(row, p.var));   // predictor.py:55-56
+                raw = decode_ref(anchor_of(p, anc, my_i), mul4(row, p.var));   // predictor.py:55-56
                 if (p.clip_decoded) raw = clip01(raw);
             } else {
                 raw = ldg_f4(p.boxes + (long long)b * p.box_stride + my_i);
@@ -1467,7 +1473,7 @@ static int launch_cluster(tfrpn_handle h, PropParams& p, int B, int cl, int thre
         if (smem > PROP_SMEM_LIMIT)
             return fail(TFRPN_ERR_UNSUPPORTED, "NMS: %d output rows need %zu B of shared memory (> %zu)", p.max_out, smem,
                         PROP_SMEM_LIMIT);
-        prof_begin(h, TFRPN_K_PROPOSAL, st);
+        prof_begin(h, TFRPN_K_PROPOSAL_CLUSTER, st);
         if (cl == 8 && threads == 512) proposal_cluster_kernel<8, 512><<<B * 8, 512, smem, st>>>(p);
         else if (cl == 8) proposal_cluster_kernel<8, 256><<<B * 8, 256, smem, st>>>(p);
         else if (cl == 4 && threads == 256) proposal_cluster_kernel<4, 256><<<B * 4, 256, smem, st>>>(p);
@@ -1706,6 +1712,44 @@ extern "C" int tfrpn_proposals(tfrpn_handle h, const float* rpn_reg, const float
     TFRPN_CHECK_ON_DEVICE(h, rpn_reg, "proposals: rpn_reg");
     return proposals_enqueue(h, rpn_reg, rpn_cls, anchors, B, N, cfg, out_boxes, out_scores, valid, keep_idx_or_null,
                              nullptr, as_stream(s));
+}
+
+// The same stage with the anchors regenerated in registers from the hyper-parameters (north star: fused
+// anchor-generate + decode + clip): no (N,4) anchor tensor is read.  N = fm_h * fm_w * n_scales * n_ratios.
+extern "C" int tfrpn_proposals_anchor_cfg(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls,
+                                          const tfrpn_anchor_cfg* acfg, int B, const tfrpn_proposal_cfg* cfg, float* out_boxes,
+                                          float* out_scores, int32_t* valid, int32_t* keep_idx_or_null, tfrpn_stream s) {
+    if (!rpn_reg || !rpn_cls || !acfg || !cfg || !out_boxes || !out_scores || !valid)
+        return fail(TFRPN_ERR_BAD_ARG, "proposals_anchor_cfg: null pointer");
+    if (B < 0) return fail(TFRPN_ERR_BAD_ARG, "proposals_anchor_cfg: negative shape");
+    if (cfg->pre_nms_topn <= 0 || cfg->post_nms_topn <= 0) return fail(TFRPN_ERR_BAD_ARG, "proposals_anchor_cfg: topn must be > 0");
+    if (!aligned16(rpn_reg) || !aligned16(out_boxes))
+        return fail(TFRPN_ERR_MISALIGNED, "proposals_anchor_cfg: rpn_reg / out_boxes must be 16-byte aligned");
+    AnchorGen gen;
+    long long N = 0;
+    if (int rc = make_anchor_gen(acfg, &gen, &N)) return rc;
+    if (B == 0) return 0;
+    if (!h) return fail(TFRPN_ERR_BAD_ARG, "proposals_anchor_cfg: null handle");
+    TFRPN_ENTER(h);
+    TFRPN_CHECK_ON_DEVICE(h, rpn_reg, "proposals_anchor_cfg: rpn_reg");
+    cudaStream_t st = as_stream(s);
+    if (!h->anchor_gen) TFRPN_CHECK_CUDA(cudaMalloc(&h->anchor_gen, sizeof(AnchorGen)));
+    if (memcmp(&h->anchor_gen_cfg, acfg, sizeof(*acfg)) != 0) {
+        // the generator lives in device memory of the handle; uploaded again only when the configuration changes
+        // (a copy from pageable memory returns once the source has been staged, so `gen` may go out of scope)
+        TFRPN_CHECK_CUDA(cudaMemcpyAsync(h->anchor_gen, &gen, sizeof(gen), cudaMemcpyHostToDevice, st));
+        TFRPN_CHECK_CUDA(cudaStreamSynchronize(st));
+        h->anchor_gen_cfg = *acfg;
+    }
+    PropParams p = {};
+    fill_proposal_params(p, rpn_reg, rpn_cls, nullptr, (int)N, cfg, out_boxes, out_scores, valid, keep_idx_or_null);
+    p.gen = static_cast<const AnchorGen*>(h->anchor_gen);
+    int k_eff = p.k;
+    if (p.max_out <= PRE_NMS_CAP_MAX_OUT) k_eff = min(p.k, PRE_NMS_CAP);
+    if (pre_applies(p.N, k_eff))   // the large-N prefilter gathers anchors from a tensor: materialise them for it
+        return fail(TFRPN_ERR_UNSUPPORTED, "proposals_anchor_cfg: N = %lld takes the prefilter path, which reads an anchor tensor; "
+                                           "call tfrpn_anchors + tfrpn_proposals", N);
+    return launch_one(h, p, B, st);
 }
 
 #ifdef TFRPN_PHASE_TIMING

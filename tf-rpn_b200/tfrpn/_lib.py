@@ -50,7 +50,7 @@ class StepBuffers(C.Structure):
 
 P = C.c_void_p
 I = C.c_int
-KERNEL_IDS = 5   # TFRPN_K_COUNT of include/tfrpn.h
+KERNEL_IDS = 6   # TFRPN_K_COUNT of include/tfrpn.h
 # name -> (restype, argtypes); must list every symbol include/tfrpn.h declares
 PROTOTYPES = {
     "tfrpn_version": (I, []),
@@ -69,6 +69,7 @@ PROTOTYPES = {
     "tfrpn_selftest_division": (I, [C.c_uint64, C.c_uint64, P, P]),
     "tfrpn_encode_deltas": (I, [P, I, P, I, I, P, P]),
     "tfrpn_decode": (I, [P, I, P, P, I, I, I, P, P]),
+    "tfrpn_decode_anchor_cfg": (I, [C.POINTER(AnchorCfg), P, P, I, I, P, P]),
     "tfrpn_scale_boxes": (I, [P, C.c_int64, C.c_float, C.c_float, I, P, P]),
     "tfrpn_rpn_targets": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, C.POINTER(TargetDebug), P]),
     "tfrpn_rpn_targets_compact": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P, P]),
@@ -80,6 +81,7 @@ PROTOTYPES = {
     "tfrpn_pad_gt": (I, [P, P, P, P, I, I, I, P, P, P]),
     "tfrpn_nms": (I, [P, P, P, I, I, C.POINTER(NmsCfg), P, P, P, P, P, P]),
     "tfrpn_proposals": (I, [P, P, P, P, I, I, C.POINTER(ProposalCfg), P, P, P, P, P]),
+    "tfrpn_proposals_anchor_cfg": (I, [P, P, P, C.POINTER(AnchorCfg), I, C.POINTER(ProposalCfg), P, P, P, P, P]),
     "tfrpn_rpn_targets_host": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P]),
     "tfrpn_proposals_host": (I, [P, P, P, P, I, I, C.POINTER(ProposalCfg), P, P, P, P, P]),
     "tfrpn_rpn_step_host": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P, P, C.POINTER(ProposalCfg), P, P, P, P, P]),

@@ -31,19 +31,39 @@ def generate_proposals(rpn_bbox_deltas, rpn_labels, anchors, hyper_params, pre_n
     -> tf.nn.top_k(k = pre_nms_topn = 6000) (:58) -> gather (:60) -> combined NMS
     (max_output_size_per_class = max_total_size = test_nms_topn = 300, iou 0.7).
     Returns (boxes (B,P,4), scores (B,P), valid_detections (B,), keep_indices (B,P) into N, -1 pad).
+
+    ``anchors=None``: the anchors of ``hyper_params`` (utils/bbox_utils.py:23-46) are regenerated in registers
+    inside the kernel -- no anchor tensor is read (feature maps below 40000 anchors).
     """
     o = Origin()
     reg = to_device(rpn_bbox_deltas, F32, o, "rpn_bbox_deltas")
     cls = to_device(rpn_labels, F32, o, "rpn_labels")
-    anc = to_device(anchors, F32, o, "anchors")
     B = reg.shape[0]
     reg = reg.reshape(B, -1, 4)
     cls = cls.reshape(B, -1)
     N = cls.shape[1]
+    cfg = proposal_cfg(hyper_params, pre_nms_topn, post_nms_topn, nms_iou_threshold, clip)
+    if anchors is None:
+        from .utils.bbox_utils import _anchor_cfg
+        acfg = _anchor_cfg(hyper_params)
+        n_cfg = acfg.fm_h * acfg.fm_w * acfg.n_scales * acfg.n_ratios
+        if reg.shape[1] != N or N != n_cfg:
+            raise ValueError("shapes disagree: deltas %s, labels %s, hyper_params give %d anchors"
+                             % (tuple(reg.shape), tuple(cls.shape), n_cfg))
+        dev = reg.device
+        P = cfg.post_nms_topn
+        boxes = torch.empty((B, P, 4), dtype=F32, device=dev)
+        scores = torch.empty((B, P), dtype=F32, device=dev)
+        valid = torch.empty((B,), dtype=torch.int32, device=dev)
+        keep = torch.empty((B, P), dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().tfrpn_proposals_anchor_cfg(_lib.handle(dev.index), ptr(reg), ptr(cls), C.byref(acfg), B,
+                                                          C.byref(cfg), ptr(boxes), ptr(scores), ptr(valid), ptr(keep),
+                                                          stream_ptr(dev)))
+        return tuple(from_device(t, o) for t in (boxes, scores, valid, keep))
+    anc = to_device(anchors, F32, o, "anchors")
     if reg.shape[1] != N or anc.shape != (N, 4):
         raise ValueError("shapes disagree: deltas %s, labels %s, anchors %s"
                          % (tuple(reg.shape), tuple(cls.shape), tuple(anc.shape)))
-    cfg = proposal_cfg(hyper_params, pre_nms_topn, post_nms_topn, nms_iou_threshold, clip)
     dev = reg.device
     P = cfg.post_nms_topn
     boxes = torch.empty((B, P, 4), dtype=F32, device=dev)

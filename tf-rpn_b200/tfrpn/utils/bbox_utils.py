@@ -131,6 +131,24 @@ def get_bboxes_from_deltas(anchors, deltas):
     return from_device(out[0] if squeeze else out, o)
 
 
+def get_bboxes_from_hyper_params(hyper_params, deltas, variances=None, clip=False):
+    """generate_anchors (utils/bbox_utils.py:23-46) fused into get_bboxes_from_deltas (:72-96): the anchors are
+    regenerated in registers, no anchor tensor is read.  ``variances`` multiplies the deltas first (predictor.py:55),
+    ``clip`` clips the boxes to [0,1].  deltas (B,N,4) or (B,F,F,4A) -> (B,N,4)."""
+    o = Origin()
+    d = to_device(deltas, F32, o, "deltas")
+    B = d.shape[0]
+    d = d.reshape(B, -1, 4)
+    cfg = _anchor_cfg(hyper_params)
+    N = cfg.fm_h * cfg.fm_w * cfg.n_scales * cfg.n_ratios
+    if d.shape[1] != N:
+        raise ValueError("deltas %s but hyper_params give %d anchors" % (tuple(d.shape), N))
+    out = torch.empty((B, N, 4), dtype=F32, device=d.device)
+    var = None if variances is None else (C.c_float * 4)(*[float(v) for v in variances])
+    _lib.check(_lib.load().tfrpn_decode_anchor_cfg(C.byref(cfg), ptr(d), var, int(bool(clip)), B, ptr(out), stream_ptr(d.device)))
+    return from_device(out, o)
+
+
 def get_deltas_from_bboxes(bboxes, gt_boxes):
     """utils/bbox_utils.py:98-124.  bboxes (N,4) or (B,N,4); gt_boxes (B,N,4) -> (B,N,4)."""
     o = Origin()
