@@ -111,7 +111,7 @@ TFRPN_API uint64_t tfrpn_launch_count(void);
 /* ---- tracing (the reference has none): when enabled, every kernel launched through
  *      this handle is bracketed by CUDA events on its stream.  Not usable during graph capture. */
 enum { TFRPN_K_IOU_ARGMAX = 0, TFRPN_K_LABEL_ENCODE = 1, TFRPN_K_SELECT_MASK = 2, TFRPN_K_PROPOSAL = 3,
-       TFRPN_K_LOSS = 4, TFRPN_K_PROPOSAL_CLUSTER = 5, TFRPN_K_COUNT = 6 };
+       TFRPN_K_LOSS = 4, TFRPN_K_PROPOSAL_CLUSTER = 5, TFRPN_K_NMS_MASK = 6, TFRPN_K_NMS_SWEEP = 7, TFRPN_K_COUNT = 8 };
 TFRPN_API int tfrpn_profile_enable(tfrpn_handle h, int on);
 /* synchronises, then returns the summed device time and launch count of one kernel id and clears them */
 TFRPN_API int tfrpn_profile_read(tfrpn_handle h, int kernel_id, double* total_ms, int* launches);

@@ -191,3 +191,50 @@ def test_decode_and_encode_ulp_bounds(T):
     want = O.get_deltas_from_bboxes(anchors, gt)
     assert bits_equal(got[..., :2], want[..., :2])
     assert within_ulps(got[..., 2:], want[..., 2:], 4)
+
+
+M = {"TFRPN_NMS_PATH": "matrix"}
+
+
+@pytest.mark.parametrize("env", [{}, M, dict(M, TFRPN_NMS_ROWS=64), dict(M, TFRPN_NMS_ROWS=256), dict(M, TFRPN_NMS_ROWS=1024),
+                                 {"TFRPN_PROP_CLUSTER": 0}, dict(M, TFRPN_PROP_CLUSTER=18)],
+                         ids=["lazy", "matrix", "matrix64_redo", "matrix256_redo", "matrix1024", "lazy_one_cta", "matrix_rank_8x256"])
+def test_nms_paths_agree_with_oracle(T, env):
+    """the lazy NMS kernels (default) and the matrix NMS (rank launch + mask + sweep), also with too few rows (every
+    image redone by the lazy kernel): the same keep lists as the oracle"""
+    hp, anchors, _, _ = config(T, "C2")
+    B, N, P = 9, anchors.shape[0], 300
+    rng = np.random.default_rng(31)
+    reg, cls = T.syn.head_outputs(rng, B, 31, 31, 9)
+    h = fresh_handle(T, **env)
+    lib = T.lib.load()
+    torch = T.torch
+    try:
+        from tfrpn.proposals import proposal_cfg
+        pc = proposal_cfg(hp, pre_nms_topn=6000)
+        ob = torch.empty((B, P, 4), device=T.dev); os_ = torch.empty((B, P), device=T.dev)
+        ov = torch.empty((B,), dtype=torch.int32, device=T.dev); ok = torch.empty((B, P), dtype=torch.int32, device=T.dev)
+        r_t, c_t, a_t = T.cu(reg.reshape(B, -1, 4)), T.cu(cls.reshape(B, -1)), T.cu(anchors)
+        st = torch.cuda.current_stream(T.dev).cuda_stream
+        T.lib.check(lib.tfrpn_proposals(h, r_t.data_ptr(), c_t.data_ptr(), a_t.data_ptr(), B, N, C.byref(pc), ob.data_ptr(),
+                                        os_.data_ptr(), ov.data_ptr(), ok.data_ptr(), st))
+        torch.cuda.synchronize()
+        wb, ws, wv, wk = CO.proposals(reg.reshape(B, -1, 4), cls.reshape(B, -1), anchors, hp, 6000)
+        assert np.array_equal(T.np(ov), wv) and np.array_equal(T.np(ok), wk)
+        assert bits_equal(T.np(os_), ws) and within_ulps(T.np(ob), wb, 4, scale=1.0)
+        # plain NMS over given boxes with a score threshold and fewer candidates than rows
+        K = 700
+        boxes, scores = T.syn.nms_boxes(rng, 3, K)
+        scores[1, 100:] = 0.001
+        nc = T.lib.NmsCfg(300, 300, 0.5, 0.01, 0, 1, 0)
+        nb = torch.empty((3, 300, 4), device=T.dev); ns = torch.empty((3, 300), device=T.dev); ncl = torch.empty((3, 300), device=T.dev)
+        nv = torch.empty((3,), dtype=torch.int32, device=T.dev); nk = torch.empty((3, 300), dtype=torch.int32, device=T.dev)
+        b_t, s_t = T.cu(boxes), T.cu(scores)
+        T.lib.check(lib.tfrpn_nms(h, b_t.data_ptr(), s_t.data_ptr(), 3, K, C.byref(nc), nb.data_ptr(), ns.data_ptr(),
+                                  ncl.data_ptr(), nv.data_ptr(), nk.data_ptr(), st))
+        torch.cuda.synchronize()
+        wb, ws, wc, wv, wk = CO.nms(boxes, scores, 300, 300, 0.5, 0.01)
+        assert np.array_equal(T.np(nv), wv) and np.array_equal(T.np(nk), wk)
+        assert bits_equal(T.np(ns), ws) and bits_equal(T.np(nb), wb)
+    finally:
+        lib.tfrpn_destroy(h)

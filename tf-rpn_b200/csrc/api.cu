@@ -153,6 +153,8 @@ extern "C" const char* tfrpn_kernel_name(int id) {
         case TFRPN_K_SELECT_MASK: return "select_mask_kernel";
         case TFRPN_K_PROPOSAL: return "proposal_kernel";
         case TFRPN_K_PROPOSAL_CLUSTER: return "proposal_cluster_kernel";
+        case TFRPN_K_NMS_MASK: return "nms_mask_kernel";
+        case TFRPN_K_NMS_SWEEP: return "nms_sweep_kernel";
         case TFRPN_K_LOSS: return "rpn_loss_partial_kernel";
         default: return "?";
     }
@@ -182,6 +184,8 @@ extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
     h->opts.pipe_trace = getenv("TFRPN_PIPE_TRACE") != nullptr;
     h->opts.pipe_gather_rows = env_int("TFRPN_PIPE_GATHER_ROWS", 0);
     h->opts.host_threads = env_int("TFRPN_HOST_THREADS", 0);
+    if (const char* g = getenv("TFRPN_NMS_PATH")) h->opts.nms_lazy = strcmp(g, "matrix") != 0;
+    h->opts.nms_rows = env_int("TFRPN_NMS_ROWS", 0);
     if (const char* g = getenv("TFRPN_PIPE_GATHER")) h->opts.pipe_gather = !strcmp(g, "host") ? 1 : (!strcmp(g, "device") ? 2 : 0);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     // device counter of the loss reduction (losses.cu): zero between calls, the kernel resets it

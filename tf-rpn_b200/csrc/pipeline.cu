@@ -61,7 +61,8 @@ int proposals_presorted_enqueue(tfrpn_handle h, const float* rpn_reg_or_null, co
                                 int compact_stride, const float* rpn_cls, const float* anchors, int B, int N,
                                 const tfrpn_proposal_cfg* cfg, int32_t* rank_idx, int32_t* rank_n, int32_t* rank_more,
                                 float* out_boxes, float* out_scores, int32_t* valid, int32_t* keep_idx_or_null,
-                                int32_t* redo_flags, unsigned long long* rows_fetched_or_null, cudaStream_t st);
+                                int32_t* redo_flags, unsigned int* mask_ws_or_null, cudaStream_t st);
+size_t proposals_mask_bytes(int B, int rows);
 int proposals_redo_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B, int N,
                            const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
                            int32_t* keep_idx_or_null, const int32_t* redo_flags, unsigned long long* rows_fetched_or_null,
@@ -187,7 +188,7 @@ struct Layout {
     size_t gt, gl, cls, small_end, reg, in_end; // inputs: the small ones first, the head's regression output last
     size_t d, l, ob, os, v, k, pc, rf, dense_end;   // results (pc: rows of rpn_reg pulled; rf: redo flags)
     size_t ci, cd, comp_end;                    // compact bbox_deltas (row indices, rows)
-    size_t ri, rn, rm, rank_end, rc, total;     // two-phase: rank indices / counts / more flags (D2H), compact rows (H2D)
+    size_t ri, rn, rm, rank_end, rc, mk, total; // two-phase: rank indices / counts / more flags (D2H), compact rows (H2D), NMS matrix
 };
 
 // everything the later stages of the step in flight need (filled by pipe_submit, read by the service thread)
@@ -294,6 +295,7 @@ static Layout make_layout(int B, int N, int G, int P) {
     L.rm = o;  o += align256((size_t)B * 4);
     L.rank_end = o;
     L.rc = o;  o += align256((size_t)B * proposals_rank_cap() * 16);   // sized for the cap: gather_rows adapts
+    L.mk = o;  o += align256(proposals_mask_bytes(B, proposals_rank_cap()));   // (device side only)
     L.total = o;
     return L;
 }
@@ -395,7 +397,7 @@ static int enqueue_tail(tfrpn_pipe* p, Slot& s) {
             TFRPN_CHECK_CUDA(cudaMemcpyAsync(d + L.rc, pin + L.rc, (size_t)B * GR * 16, cudaMemcpyHostToDevice, s.s_prop));
         }
         if (int rc = proposals_presorted_enqueue(h, nullptr, reinterpret_cast<const float*>(d + L.rc), GR, GR, cls, st.anchors,
-                                                 B, N, &st.pcfg, ri, rn, rm, ob, os, v, k, rf, nullptr, s.s_prop)) return rc;
+                                                 B, N, &st.pcfg, ri, rn, rm, ob, os, v, k, rf, reinterpret_cast<unsigned int*>(d + L.mk), s.s_prop)) return rc;
         // images whose NMS ran out of gathered rows (rare): the unfiltered kernel redoes them, reading the rows it
         // needs straight from the caller's page-locked tensor; a pageable tensor is handled when the step is retired
         if (st.reg_pinned) {

@@ -20,6 +20,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -100,7 +102,11 @@ struct PropParams {
     int compact_rows;           //   ranks >= compact_rows read `reg`, or end the batch when `reg` is null
     int compact_stride;
     int* redo_flags;            // presorted out (B,): 1 = the batch ran out before max_out boxes were kept (the
-};                              //   unfiltered kernel must redo the image), else 0
+                                //   unfiltered kernel must redo the image), else 0
+    // matrix NMS (nms_mask_kernel + nms_sweep_kernel) over the first nms_rows ranks of the rank launch
+    unsigned int* nms_mask;     // (B, nms_rows, mask_words): bit j%32 of word j/32 of row i set iff j < i and j suppresses i
+    int nms_rows, mask_words;
+};
 
 struct PropShared {
     unsigned int hist[256];
@@ -715,6 +721,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
     unsigned long long lo_tau = 0ull;       // entries already consumed: composite >= lo_tau
     bool have_lo = false;
     int par = 0;                            // parity of the NMS round (cluster-uniform)
+    if (p.mode == MODE_RANK && K <= 0 && tid == 0 && crank == 0) { p.rank_n[b] = 0; p.rank_more[b] = 0; }   // no rank at all
 
     for (int lo = 0; lo < K;) {
         auto eligible = [&](unsigned long long c) -> bool { return !have_lo || c < lo_tau; };
@@ -1093,6 +1100,202 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
     PH_FLUSH;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Matrix NMS over the ranks a MODE_RANK launch produced.  The lazy kernels above do the minimum number of pair
+// tests but on one or two SMs per image with a barrier between every phase (25 % of the issue capacity of
+// the SMs they hold).  Here the pair tests of the first T = nms_rows ranks are done up front by the whole GPU,
+//   nms_mask_kernel    CTA (word w, image b): the 32 boxes of ranks [32w, 32w+32) in shared memory; every thread
+//                      owns a later rank i and packs "j suppresses i" of those 32 predecessors into one word
+//   nms_sweep_kernel   one 128-thread CTA per image walks the ranks in chunks of 128: a candidate is dead if a row
+//                      word ANDed with the kept bits of the earlier chunks is non-zero, the chunk itself is resolved
+//                      with the same parallel sweeps as above, kept boxes are decoded again and written out
+// ~1.5x the pair tests of the lazy kernel (205 k instead of 138 k per image at C2, T = 640), no dependency
+// between them.  An image that has not filled max_out when the T ranks are used up raises redo_flags[b] and
+// the lazy kernel redoes it.  Results are bit-identical: same composites, same order, same pair test.
+// Measured at C2 (profiles/r2g_*): rank launch 11.7 us + mask 31 us (14.0 M warp instructions, 34 per pair test)
+// + sweep 19 us against 43.6 us for the lazy kernel, and MORE instructions in total (20 M vs 12 M per launch), so
+// with several steps in flight the GPU -- which is issue-bound -- loses throughput (1.28 M vs 1.37 M images/s).
+// The path is therefore opt-in (TFRPN_NMS_PATH=matrix); the lazy kernels stay the default.
+// ------------------------------------------------------------------------------------------------
+constexpr int MASK_THREADS = 256;
+constexpr int SWEEP_THREADS = NMS_CHUNK;   // 128
+
+// raw (decoded, optionally clipped) box of the entry `idx` at rank `rank` of image b
+__device__ __forceinline__ float4 ranked_raw_box(const PropParams& p, int b, int rank, uint32_t idx) {
+    if (p.mode == MODE_PROPOSALS) {
+        const float4 row = (p.reg_compact && rank < p.compact_rows)
+                               ? ldg_f4(p.reg_compact + (long long)b * p.compact_stride + rank)
+                               : ldg_f4(p.reg + (long long)b * p.N + idx);
+        const float4* anc = p.anchors + (p.anchors_batched ? (long long)b * p.N : 0LL);
+        float4 raw = decode_ref(anchor_of(p, anc, idx), mul4(row, p.var));   // predictor.py:55-56
+        return p.clip_decoded ? clip01(raw) : raw;
+    }
+    return ldg_f4(p.boxes + (long long)b * p.box_stride + idx);
+}
+__device__ __forceinline__ void canonical_box(float4 raw, const IouThreshold& thr, float4& c, float& ca) {
+    c = make_float4(fminf(raw.x, raw.z), fminf(raw.y, raw.w), fmaxf(raw.x, raw.z), fmaxf(raw.y, raw.w));
+    ca = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
+    if (thr.fast && !(ca > 0.0f)) { c = TFRPN_FAR_BOX; ca = 0.0f; }   // see nms_suppresses_fast
+}
+// ranks of image b the matrix covers, and whether the image has ranks beyond them
+__device__ __forceinline__ int matrix_rows(const PropParams& p, int b, bool& more) {
+    int n = p.rank_n[b];
+    more = p.rank_more[b] != 0;
+    int cap = p.nms_rows;
+    if (p.reg_compact && p.compact_rows < cap) cap = p.compact_rows;   // only the gathered rows can be decoded
+    if (n > cap) { n = cap; more = true; }
+    return n;
+}
+
+__global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(const __grid_constant__ PropParams p) {
+    __shared__ float4 jbox[32];
+    __shared__ float jarea[32];
+    const int b = blockIdx.y, w = blockIdx.x, tid = threadIdx.x;
+    bool more;
+    const int n = matrix_rows(p, b, more);
+    if (32 * w + 1 >= n) return;                 // no rank of this image has a predecessor in this word
+    const IouThreshold thr = p.iou_thr;
+    const int* ridx = p.rank_idx + (long long)b * BATCH;
+    if (tid < 32) {
+        const int j = 32 * w + tid;
+        float4 c = TFRPN_FAR_BOX;
+        float ca = 0.0f;
+        if (j < n) canonical_box(ranked_raw_box(p, b, j, (uint32_t)ridx[j]), thr, c, ca);
+        jbox[tid] = c;
+        jarea[tid] = ca;
+    }
+    __syncthreads();
+    unsigned int* mrow = p.nms_mask + (long long)b * p.nms_rows * p.mask_words + w;
+    for (int i = 32 * w + 1 + tid; i < n; i += MASK_THREADS) {
+        float4 ci;
+        float ai;
+        canonical_box(ranked_raw_box(p, b, i, (uint32_t)ridx[i]), thr, ci, ai);
+        const int jmax = min(32, i - 32 * w);    // predecessors of i inside this word
+        unsigned int word = 0u;
+        if (thr.fast) {
+            if (jmax == 32) {
+#pragma unroll 8
+                for (int jj = 0; jj < 32; ++jj)
+                    word |= nms_suppresses_fast(jbox[jj], jarea[jj], ci, ai, thr) ? (1u << jj) : 0u;
+            } else {
+                for (int jj = 0; jj < jmax; ++jj)
+                    word |= nms_suppresses_fast(jbox[jj], jarea[jj], ci, ai, thr) ? (1u << jj) : 0u;
+            }
+        } else {
+            for (int jj = 0; jj < jmax; ++jj)
+                word |= nms_suppresses(jbox[jj], jarea[jj], ci, ai, thr) ? (1u << jj) : 0u;
+        }
+        mrow[(long long)i * p.mask_words] = word;
+    }
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS) nms_sweep_kernel(const __grid_constant__ PropParams p) {
+    __shared__ unsigned int kw[BATCH / 32];      // kept bits by rank
+    __shared__ uint4 pr_s[NMS_CHUNK];            // predecessor words of the chunk's candidates (inside the chunk)
+    __shared__ unsigned int dead_s[4];
+    __shared__ int slot[NMS_CHUNK];
+    __shared__ int s_nk;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    bool more;
+    const int n = matrix_rows(p, b, more);
+    const int W = p.mask_words;
+    const int* ridx = p.rank_idx + (long long)b * BATCH;
+    const float* scores = p.scores + (long long)b * p.N;
+    const unsigned int* mimg = p.nms_mask + (long long)b * p.nms_rows * W;
+    if (tid < BATCH / 32) kw[tid] = 0u;
+    if (tid < 4) dead_s[tid] = 0u;
+    __syncthreads();
+    int nkept = 0;
+    for (int pos = 0; pos < n && nkept < p.max_out; pos += NMS_CHUNK) {
+        const int C = min(NMS_CHUNK, n - pos);
+        const int i = pos + tid;
+        const int w0 = pos >> 5;                 // first word of this chunk
+        bool dead = false;
+        uint4 pr = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < C) {
+            const unsigned int* row = mimg + (long long)i * W;
+            const int wlast = (i - 1) >> 5;      // last word the mask kernel wrote for row i (i >= 1), -1 for i == 0
+            unsigned int hit = 0u;
+            for (int w = 0; w < w0; ++w) hit |= row[w] & kw[w];
+            dead = hit != 0u;
+            if (i > 0) {
+                pr.x = (w0 <= wlast) ? row[w0] : 0u;
+                pr.y = (w0 + 1 <= wlast) ? row[w0 + 1] : 0u;
+                pr.z = (w0 + 2 <= wlast) ? row[w0 + 2] : 0u;
+                pr.w = (w0 + 3 <= wlast) ? row[w0 + 3] : 0u;
+            }
+            pr_s[tid] = pr;
+            if (dead) atomicOr(&dead_s[tid >> 5], 1u << (tid & 31));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // the chunk's greedy order resolved in parallel sweeps (see proposal_kernel): lane l owns candidates
+            // l, 32 + l, 64 + l, 96 + l
+            uint4 q4[4];
+            unsigned U[4], Kp[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                q4[q] = pr_s[q * 32 + lane];
+                U[q] = __ballot_sync(0xffffffffu, q * 32 + lane < C) & ~dead_s[q];
+            }
+            while ((U[0] | U[1] | U[2] | U[3]) != 0u) {
+                unsigned nU[4], nK[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool und = (U[q] >> lane) & 1u;
+                    const unsigned hitK = (q4[q].x & Kp[0]) | (q4[q].y & Kp[1]) | (q4[q].z & Kp[2]) | (q4[q].w & Kp[3]);
+                    const unsigned hitU = (q4[q].x & U[0]) | (q4[q].y & U[1]) | (q4[q].z & U[2]) | (q4[q].w & U[3]);
+                    nK[q] = __ballot_sync(0xffffffffu, und && hitK == 0u && hitU == 0u);
+                    nU[q] = __ballot_sync(0xffffffffu, und && hitK == 0u && hitU != 0u);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { Kp[q] |= nK[q]; U[q] = nU[q]; }
+            }
+            // kept candidates take consecutive output slots in score order, capped at max_out
+            const int allowed = p.max_out - nkept;
+            int before = 0;
+            unsigned keptw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int rk = before + __popc(Kp[q] & ((1u << lane) - 1u));
+                const bool kept = ((Kp[q] >> lane) & 1u) && rk < allowed;
+                slot[q * 32 + lane] = kept ? nkept + rk : -1;
+                keptw[q] = __ballot_sync(0xffffffffu, kept);
+                before += __popc(Kp[q]);
+            }
+            if (lane < 4) {
+                kw[w0 + lane] = lane == 0 ? keptw[0] : lane == 1 ? keptw[1] : lane == 2 ? keptw[2] : keptw[3];
+                dead_s[lane] = 0u;
+            }
+            if (lane == 0) s_nk = min(before, allowed);
+        }
+        __syncthreads();
+        if (tid < C && slot[tid] >= 0) {
+            const uint32_t idx = (uint32_t)ridx[i];
+            const float4 raw = ranked_raw_box(p, b, i, idx);
+            const long long o = (long long)b * p.rows + slot[tid];
+            p.out_boxes[o] = p.clip_out ? clip01(raw) : raw;
+            p.out_scores[o] = scores[idx];
+            if (p.keep_idx) p.keep_idx[o] = (int)idx;
+        }
+        nkept += s_nk;
+        __syncthreads();
+    }
+    const bool redo = nkept < p.max_out && more;
+    if (tid == 0) p.redo_flags[b] = redo ? 1 : 0;
+    if (redo) return;                            // the lazy kernel redoes this image and writes all of its outputs
+    for (int rnk = tid; rnk < p.rows; rnk += SWEEP_THREADS) {   // zero padding (TF); keep_idx pads with -1
+        const long long o = (long long)b * p.rows + rnk;
+        if (rnk >= nkept) {
+            p.out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+            p.out_scores[o] = 0.0f;
+            if (p.keep_idx) p.keep_idx[o] = -1;
+        }
+        if (p.out_classes) p.out_classes[o] = 0.0f;
+    }
+    if (tid == 0) p.valid[b] = nkept;
+}
+
 static size_t cluster_smem_bytes(int cl, int n_staged, int max_out) {
     max_out = (max_out + 3) & ~3;
     const int T = 1024 / cl;                        // (sort slots per CTA)
@@ -1386,10 +1589,12 @@ static bool pre_applies(int N, int k) {
     return !off && k > 0 && N >= PRE_MIN_N && (long long)k * 4 <= N;
 }
 static size_t prefilter_bytes_for(int B, int N, int k);
-size_t prefilter_workspace_bytes(int B, int N, int k) {
+size_t matrix_workspace_bytes(int B);
+size_t prefilter_workspace_bytes(int B, int N, int k) {   // = the proposal side's workspace: prefilter arrays or the NMS matrix
     if (k <= 0) k = N;
     const size_t a = prefilter_bytes_for(B, N, k), b = prefilter_bytes_for(B, N, min(k, PRE_NMS_CAP));
-    return a > b ? a : b;
+    const size_t c = B > 0 ? matrix_workspace_bytes(B) : 0;
+    return std::max(std::max(a, b), c);
 }
 static size_t prefilter_bytes_for(int B, int N, int k) {
     if (B <= 0 || !pre_applies(N, k)) return 0;
@@ -1404,6 +1609,7 @@ static size_t prefilter_bytes_for(int B, int N, int k) {
 }
 
 static int launch_one(tfrpn_handle h, PropParams& p, int B, cudaStream_t st);
+static int launch_cluster(tfrpn_handle h, PropParams& p, int B, int cl, int threads, cudaStream_t st);
 
 static int launch_prefiltered(tfrpn_handle h, PropParams& p, int k_eff, int B, cudaStream_t st) {
     const int N = p.N, Mcap = min(N, k_eff + PRE_SLACK);
@@ -1457,10 +1663,59 @@ static int launch_prefiltered(tfrpn_handle h, PropParams& p, int k_eff, int B, c
     return launch_one(h, c2, B, st);
 }
 
+// ---- matrix NMS launch sequence (small N): rank launch -> mask -> sweep -> lazy kernel for flagged images ----
+static int matrix_rows_of(tfrpn_handle h) {
+    int r = h->opts.nms_rows > 0 ? h->opts.nms_rows : 640;
+    r = (r + 31) & ~31;
+    return r < 32 ? 32 : (r > BATCH ? BATCH : r);
+}
+size_t matrix_workspace_bytes(int B) {   // sized for the largest row count, so TFRPN_NMS_ROWS never outgrows a reservation
+    return align256((size_t)B * BATCH * 4) + 3 * align256((size_t)B * 4) + align256((size_t)B * BATCH * (BATCH / 32) * 4) + 256;
+}
+static bool matrix_applies(tfrpn_handle h, const PropParams& p) {
+    if (!h || h->opts.nms_lazy || p.mode == MODE_TOPK || p.counts || p.remap || p.flag_mode != 0 || p.presorted) return false;
+    return p.max_out >= 1 && cluster_smem_bytes(2, p.N, p.max_out) <= PROP_SMEM_LIMIT;   // the rank launch stages every key
+}
+// mask + sweep over ranks already produced (rank_idx / rank_n / rank_more set in p); `mask` holds B * rows * rows/32 words
+static int launch_mask_sweep(tfrpn_handle h, PropParams& p, int B, int rows, unsigned int* mask, cudaStream_t st) {
+    p.nms_mask = mask; p.nms_rows = rows; p.mask_words = rows / 32;
+    prof_begin(h, TFRPN_K_NMS_MASK, st);
+    nms_mask_kernel<<<dim3(p.mask_words, B), MASK_THREADS, 0, st>>>(p);
+    prof_end(h, st);
+    TFRPN_AFTER_LAUNCH("nms_mask_kernel");
+    prof_begin(h, TFRPN_K_NMS_SWEEP, st);
+    nms_sweep_kernel<<<B, SWEEP_THREADS, 0, st>>>(p);
+    prof_end(h, st);
+    TFRPN_AFTER_LAUNCH("nms_sweep_kernel");
+    return 0;
+}
+static void two_phase_shape(tfrpn_handle h, int B, int& cl, int& threads);
+static int launch_matrix(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
+    char* ws = nullptr;
+    if (int rc = ensure_workspace_prop(h, matrix_workspace_bytes(B), st, &ws)) return rc;
+    int32_t* rank_idx = reinterpret_cast<int32_t*>(ws); ws += align256((size_t)B * BATCH * 4);
+    int32_t* rank_n = reinterpret_cast<int32_t*>(ws); ws += align256((size_t)B * 4);
+    int32_t* rank_more = reinterpret_cast<int32_t*>(ws); ws += align256((size_t)B * 4);
+    int32_t* redo = reinterpret_cast<int32_t*>(ws); ws += align256((size_t)B * 4);
+    unsigned int* mask = reinterpret_cast<unsigned int*>(ws);
+    PropParams r = p;
+    r.mode = MODE_RANK; r.rank_idx = rank_idx; r.rank_n = rank_n; r.rank_more = rank_more;
+    int cl, threads;
+    two_phase_shape(h, B, cl, threads);
+    if (int rc = launch_cluster(h, r, B, cl, threads, st)) return rc;
+    PropParams m = p;
+    m.rank_idx = rank_idx; m.rank_n = rank_n; m.rank_more = rank_more; m.redo_flags = redo;
+    if (int rc = launch_mask_sweep(h, m, B, matrix_rows_of(h), mask, st)) return rc;
+    PropParams c2 = p;   // images that used up the matrix rows before max_out boxes were kept (rare)
+    c2.flags = redo; c2.flag_mode = 2;
+    return launch_one(h, c2, B, st);
+}
+
 static int launch(tfrpn_handle h, PropParams& p, int B, cudaStream_t st) {
     int k_eff = p.k;
     if (p.mode != MODE_TOPK && p.max_out <= PRE_NMS_CAP_MAX_OUT) k_eff = min(p.k, PRE_NMS_CAP);
     if (h && pre_applies(p.N, k_eff)) return launch_prefiltered(h, p, k_eff, B, st);
+    if (matrix_applies(h, p)) return launch_matrix(h, p, B, st);
     return launch_one(h, p, B, st);
 }
 
@@ -1651,19 +1906,23 @@ int proposals_presorted_enqueue(tfrpn_handle h, const float* rpn_reg_or_null, co
                                 int compact_stride, const float* rpn_cls, const float* anchors, int B, int N,
                                 const tfrpn_proposal_cfg* cfg, int32_t* rank_idx, int32_t* rank_n, int32_t* rank_more,
                                 float* out_boxes, float* out_scores, int32_t* valid, int32_t* keep_idx_or_null,
-                                int32_t* redo_flags, unsigned long long* rows_fetched_or_null, cudaStream_t st) {
+                                int32_t* redo_flags, unsigned int* mask_ws_or_null, cudaStream_t st) {
     PropParams p = {};
     fill_proposal_params(p, rpn_reg_or_null, rpn_cls, anchors, N, cfg, out_boxes, out_scores, valid, keep_idx_or_null);
-    p.rows_fetched = rows_fetched_or_null;
-    p.presorted = 1;
     p.rank_idx = rank_idx; p.rank_n = rank_n; p.rank_more = rank_more;
     p.reg_compact = reinterpret_cast<const float4*>(reg_compact); p.compact_rows = reg_compact ? compact_rows : 0;
     p.compact_stride = compact_stride;
     p.redo_flags = redo_flags;
+    if (mask_ws_or_null && !h->opts.nms_lazy) {   // matrix NMS over the gathered rows (the caller owns the mask buffer)
+        int rows = (min(compact_rows, BATCH) + 31) & ~31;
+        return launch_mask_sweep(h, p, B, rows, mask_ws_or_null, st);
+    }
+    p.presorted = 1;                              // the lazy cluster kernel's rounds over the same ranks
     int cl, threads;
     two_phase_shape(h, B, cl, threads);
     return launch_cluster(h, p, B, cl, threads, st);
 }
+size_t proposals_mask_bytes(int B, int rows) { rows = (min(rows, BATCH) + 31) & ~31; return (size_t)B * rows * (rows / 32) * 4; }
 int proposals_gather_enqueue(const float* reg_pinned_dev, const int32_t* rank_idx, const int32_t* rank_n, int B, int N,
                              int rows, float* dst, int stride, unsigned long long* counter_or_null, cudaStream_t st) {
     const dim3 grid((2 * rows + 255) / 256, B);

@@ -50,7 +50,7 @@ class StepBuffers(C.Structure):
 
 P = C.c_void_p
 I = C.c_int
-KERNEL_IDS = 6   # TFRPN_K_COUNT of include/tfrpn.h
+KERNEL_IDS = 8   # TFRPN_K_COUNT of include/tfrpn.h
 # name -> (restype, argtypes); must list every symbol include/tfrpn.h declares
 PROTOTYPES = {
     "tfrpn_version": (I, []),

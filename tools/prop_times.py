@@ -10,9 +10,15 @@ from tfrpn.utils import bbox_utils, train_utils
 dev = torch.device("cuda:0")
 lib = _lib.load(); h = _lib.handle(0)
 def read():
-    tot, n = C.c_double(), C.c_int()
-    _lib.check(lib.tfrpn_profile_read(h, 3, C.byref(tot), C.byref(n)))
-    return 1e3 * tot.value / max(n.value, 1)
+    parts, total, launches = [], 0.0, 1
+    for kid in (3, 5, 6, 7):   # lazy one-CTA kernel, cluster kernel (lazy or rank launch), mask, sweep
+        tot, n = C.c_double(), C.c_int()
+        _lib.check(lib.tfrpn_profile_read(h, kid, C.byref(tot), C.byref(n)))
+        if n.value:
+            parts.append("%s %.1f" % (lib.tfrpn_kernel_name(kid).decode().replace("_kernel", ""), 1e3 * tot.value / n.value))
+            total += 1e3 * tot.value
+            launches = max(launches, n.value)
+    return "%.1f us (%s)" % (total / launches, ", ".join(parts))
 out = []
 for name, hp_over, fm, B in (("C1", {}, (31, 31), 1), ("C2", {}, (31, 31), 64), ("C2b128", {}, (31, 31), 128),
                              ("C4", {"img_size": (800, 1333), "feature_map_shape": (50, 84)}, (50, 84), 32)):
@@ -29,7 +35,7 @@ for name, hp_over, fm, B in (("C1", {}, (31, 31), 1), ("C2", {}, (31, 31), 64), 
     _lib.check(lib.tfrpn_profile_enable(h, 1))
     for i in range(24):
         tfrpn.generate_proposals(sets[i % 4][0], sets[i % 4][1], anchors, hp)
-    out.append("%s(B=%d) %.1f us" % (name, B, read()))
+    out.append("%s(B=%d) %s" % (name, B, read()))
     _lib.check(lib.tfrpn_profile_enable(h, 0))
 for K in (20000, 200000):
     rng = np.random.default_rng(K)
@@ -42,6 +48,6 @@ for K in (20000, 200000):
         _lib.check(lib.tfrpn_profile_enable(h, 1))
         for i in range(10):
             bbox_utils.non_max_suppression(tb, ts, max_output_size_per_class=300, max_total_size=300, iou_threshold=0.7, **kw)
-        out.append("C5 K=%d %s %.1f us" % (K, mode, read()))
+        out.append("C5 K=%d %s %s" % (K, mode, read()))
         _lib.check(lib.tfrpn_profile_enable(h, 0))
 print(" | ".join(out))
