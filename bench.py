@@ -586,6 +586,32 @@ def run_ours(args):
             t = float(tt.item())
         return t
 
+    # ---- the optional final gather of targets and proposals (north star: the only NCCL traffic; NOT part of `value`) ----
+    final_gather = None
+    if world > 1 and rpn:
+        from tfrpn import sharding
+        s0 = sets[0]
+        parts = [s0["deltas"], s0["labels"], s0["pb"], s0["ps"], s0["pv"], s0["pk"]]
+        outs_g = [torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in parts]
+        for t, o in zip(parts, outs_g):
+            sharding.gather_equal(t, o)
+        barrier()
+        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ga.record()
+        for _ in range(20):
+            for t, o in zip(parts, outs_g):
+                sharding.gather_equal(t, o)
+        gb.record()
+        torch.cuda.synchronize()
+        gms = torch.tensor([ga.elapsed_time(gb) / 20], device=dev)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        by = sum(t.numel() * t.element_size() for t in parts)
+        final_gather = {"ms_per_step": float(gms.item()), "bytes_per_rank": by, "tensors": 6,
+                        "algbw_gbs_per_rank": by * (world - 1) / (float(gms.item()) * 1e-3) / 1e9,
+                        "api": "tfrpn.sharding.gather_equal (torch.distributed all_gather_into_tensor, NCCL): dense bbox_deltas, "
+                               "bbox_labels and the four proposal tensors of one step; optional, outside `value`"}
+        del outs_g
+
     if rpn:
         e2e = e2e_rpn(args, wl, lib, _lib, h, hp, anchors, np_sets, tcfg, pcfg, wall, world, rank, dev, K)
     else:
@@ -603,6 +629,8 @@ def run_ours(args):
             "p50_ms": p50, "p90_ms": p90, "host_enqueue_ms_per_step": t_host * 1e3 / K, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches_per_step * K),
             "roofline": roofline, "kernels": kernels}
+    if final_gather is not None:
+        line["final_gather"] = final_gather
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import rpn_oracle

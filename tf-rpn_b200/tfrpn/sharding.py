@@ -35,6 +35,16 @@ def sharded_proposals(rpn_bbox_deltas, rpn_labels, anchors, hyper_params, rank, 
     return generate_proposals(reg, cls, anchors, hyper_params, **kw)
 
 
+def gather_equal(local, out=None, group=None):
+    """All-gather of equally sized row blocks into one (world * rows, ...) tensor in rank order: a single
+    ``all_gather_into_tensor`` (NCCL: one kernel over NVLink; no padding, no concatenation)."""
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
 def gather_rows(local, batch, group=None):
     """All-gather variable-sized row blocks back into the global batch order (ragged-safe)."""
     world = dist.get_world_size(group)

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""e2e images/s of tfrpn.HostPipeline at C2 under torchrun (one rank per GPU), for several host-side policies, in one
+process group: who gathers the candidate rows (host threads / device), how many pool threads, dense input.
+   python -m torch.distributed.run --nproc-per-node N tools/e2e_scale.py [depth]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tf-rpn_b200"))
+import numpy as np, torch, torch.distributed as dist
+import tfrpn
+from tfrpn import synthetic
+from tfrpn.utils import train_utils
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+DEPTH = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+B, G = 64, 50
+hp = dict(train_utils.get_hyper_params("vgg16"))
+rng = np.random.default_rng(1 + rank)
+gtb, gtl = synthetic.gt_batch(rng, B, G)
+reg, cls = synthetic.head_outputs(rng, B, 31, 31, 9)
+modes = [("auto", {}),
+         ("device gather", {"TFRPN_PIPE_GATHER": "device"}),
+         ("host gather, 2 threads", {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": "2"}),
+         ("host gather, 3 threads", {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": "3"}),
+         ("host gather, 4 threads", {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": "4"}),
+         ("dense input, compact output", {"TFRPN_PIPE_DENSE_IN": "1"}),
+         ("targets only (auto)", {"_mode": "targets"}),
+         ("proposals only, device gather", {"TFRPN_PIPE_GATHER": "device", "_mode": "proposals"}),
+         ("proposals only, host gather 3", {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": "3", "_mode": "proposals"})]
+def barrier():
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+for name, env in modes:
+    mode = env.pop("_mode", "both")
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    pipe = tfrpn.HostPipeline(hp, depth=DEPTH, device=dev, pre_nms_topn=6000)
+    for k, v in old.items():
+        if v is None: os.environ.pop(k, None)
+        else: os.environ[k] = v
+    for i in range(DEPTH):
+        v = pipe.acquire(B, G)
+        v.gt_boxes[...], v.gt_labels[...], v.rpn_reg[...], v.rpn_cls[...] = gtb, gtl, reg, cls
+        pipe.submit(offset=i)
+    pipe.drain()
+    def run(n):
+        tk = []
+        for i in range(n):
+            if i >= DEPTH - 1: pipe.wait(tk[i - (DEPTH - 1)])
+            pipe.acquire(B, G)
+            tk.append(pipe.submit(targets=mode != "proposals", proposals=mode != "targets", offset=i))
+        pipe.drain()
+    run(30)
+    barrier()
+    t0 = time.perf_counter(); n = 300; run(n); torch.cuda.synchronize(); t = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t], device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t = float(tt.item())
+    if rank == 0:
+        print("%d GPUs, depth %d, %-34s: %.1f us/step per GPU, %.0f images/s in total, copy bytes %s"
+              % (world, DEPTH, name, 1e6 * t / n, world * B * n / t, pipe.last_copy_bytes()), flush=True)
+    pipe.close()
+if world > 1:
+    dist.destroy_process_group()
