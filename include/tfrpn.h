@@ -171,6 +171,16 @@ TFRPN_API int tfrpn_rpn_targets_compact(tfrpn_handle h, const float* anchors, co
                               const int32_t* gt_labels, int B, int N, int G, const tfrpn_target_cfg* cfg,
                               float* labels /* (B,N) */, int32_t* pos_idx /* (B,total_pos) */,
                               float* pos_deltas /* (B,total_pos,4) */, tfrpn_stream s);
+/* Fully sparse form: bbox_labels is -1 everywhere except the <= total_pos + total_neg sampled entries
+ * (utils/train_utils.py:126-133), so it travels as codes 2 * anchor + label (label 1 or 0), in no particular order,
+ * unused slots -1: ~1 KB per image instead of 4 * N bytes.  tfrpn_expand_labels_host rebuilds the dense tensor; with
+ * prev_codes (the codes of the step whose labels `labels` still holds) only those entries are reset first. */
+TFRPN_API int tfrpn_rpn_targets_sparse(tfrpn_handle h, const float* anchors, const float* gt_boxes,
+                             const int32_t* gt_labels, int B, int N, int G, const tfrpn_target_cfg* cfg,
+                             int32_t* label_codes /* (B,total_pos+total_neg) */, int32_t* pos_idx /* (B,total_pos) */,
+                             float* pos_deltas /* (B,total_pos,4) */, tfrpn_stream s);
+TFRPN_API int tfrpn_expand_labels_host(const int32_t* label_codes, int B, int N, int Q,
+                             const int32_t* prev_codes_or_null, int prev_Q, float* labels /* (B,N) host */);
 TFRPN_API int tfrpn_expand_targets_host(const int32_t* pos_idx, const float* pos_deltas, int B, int N, int total_pos,
                               const int32_t* prev_pos_idx_or_null, int prev_total_pos,
                               float* deltas /* (B,N,4) host */);

@@ -116,12 +116,21 @@ def test_acquired_device_side_gather(cuda_device):
     run_acquired(cuda_device, 5, 9, 3, 4, {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": 2})
 
 
+def test_acquired_sparse_labels(cuda_device):
+    """TFRPN_PIPE_SPARSE_LABELS=1: bbox_labels returns as codes of its <= 256 entries != -1 per image and the host threads
+    keep the slot's dense array consistent from step to step (slots are reused: depth 2, 6 steps)"""
+    copied = run_acquired(cuda_device, 64, 50, 4, 9, {"TFRPN_PIPE_SPARSE_LABELS": 1})
+    assert copied[-1][1] < 64 * 8649 * 4 // 2
+    run_acquired(cuda_device, 6, 9, 2, 6, {"TFRPN_PIPE_SPARSE_LABELS": 1, "TFRPN_PIPE_GATHER": "device", "TFRPN_HOST_THREADS": 2})
+    run_acquired(cuda_device, 6, 9, 2, 6, {"TFRPN_PIPE_SPARSE_LABELS": 0})
+
+
 def test_acquired_dense_input_switch_equals_two_phase(cuda_device):
     run_acquired(cuda_device, 7, 5, 3, 4, {"TFRPN_PIPE_DENSE_IN": 1})
     run_acquired(cuda_device, 7, 5, 3, 4, {"TFRPN_PIPE_DENSE": 1})
 
 
-@pytest.mark.parametrize("gather_rows", [0, 96])
+@pytest.mark.parametrize("gather_rows", [0, 96, -1])
 @pytest.mark.parametrize("pinned", [False, True])
 def test_submit_caller_buffers_two_phase(cuda_device, gather_rows, pinned):
     """tfrpn_pipeline_submit with the caller's own arrays (pageable: the gather reads them in place, flagged images
@@ -135,7 +144,7 @@ def test_submit_caller_buffers_two_phase(cuda_device, gather_rows, pinned):
     anchors = torch.from_numpy(anchors_np).to(cuda_device)
     B, G, N, P = 5, 8, 8649, 300
     lib = _lib.load()
-    env = {"TFRPN_PIPE_GATHER_ROWS": gather_rows} if gather_rows else {}
+    env = {"TFRPN_PIPE_GATHER_ROWS": gather_rows} if gather_rows > 0 else ({"TFRPN_PIPE_SPARSE_LABELS": 1} if gather_rows else {})
     h = C.c_void_p()
     with Env(**env):
         _lib.check(lib.tfrpn_create(C.byref(h), cuda_device.index or 0))

@@ -48,7 +48,7 @@ namespace tfrpn {
 size_t targets_workspace_bytes(int B, int N, int G);  // targets.cu
 int launch_targets(tfrpn_handle h, const float* anchors, const float* gt_boxes, const int32_t* gt_labels, int B, int N,
                    int G, const tfrpn_target_cfg* cfg, float* deltas, float* labels, int32_t* pos_idx,
-                   float* pos_deltas, const tfrpn_target_debug* dbg, tfrpn_stream s);
+                   float* pos_deltas, int32_t* lbl_code, const tfrpn_target_debug* dbg, tfrpn_stream s);
 int proposals_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B, int N,
                       const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
                       int32_t* keep_idx_or_null, unsigned long long* rows_fetched_or_null, cudaStream_t st);   // proposals.cu
@@ -75,7 +75,8 @@ namespace {
 
 constexpr int MAX_CHUNKS = 8;
 constexpr int MAX_DEPTH = 16;
-constexpr int COMPACT_MAX_POS = 256;   // compact result form is used when total_pos_bboxes <= this
+constexpr int COMPACT_MAX_POS = 256;   // sparse result form is used when total_pos_bboxes <= this ...
+constexpr int COMPACT_MAX_Q = 512;     // ... and total_pos_bboxes + total_neg_bboxes <= this
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -187,17 +188,18 @@ class HostPool {
 struct Layout {
     size_t gt, gl, cls, small_end, reg, in_end; // inputs: the small ones first, the head's regression output last
     size_t d, l, ob, os, v, k, pc, rf, dense_end;   // results (pc: rows of rpn_reg pulled; rf: redo flags)
-    size_t ci, cd, comp_end;                    // compact bbox_deltas (row indices, rows)
+    size_t comp, comp_end;                      // sparse targets (label codes, row indices, rows: packed at submit)
     size_t ri, rn, rm, rank_end, rc, mk, total; // two-phase: rank indices / counts / more flags (D2H), compact rows (H2D), NMS matrix
 };
 
 // everything the later stages of the step in flight need (filled by pipe_submit, read by the service thread)
 struct Step {
-    bool do_t = false, do_p = false, acquired = false, compact = false, two_phase = false;
+    bool do_t = false, do_p = false, acquired = false, compact = false, two_phase = false, sparse_labels = false;
     bool reg_pinned = false;            // the caller's rpn_reg is page-locked: the device can read it (redo pulls rows)
     bool device_gather = false;         // the rows are gathered by a kernel reading the page-locked tensor (no host stage)
-    int B = 0, N = 0, G = 0, P = 0, GR = 0, total_pos = 0;
+    int B = 0, N = 0, G = 0, P = 0, GR = 0, total_pos = 0, Q = 0;
     Layout L = {};
+    size_t cl = 0, ci = 0, cd = 0;      // sparse targets inside [L.comp, L.comp_end): label codes (B,Q), row indices (B,total_pos), rows
     const float* anchors = nullptr;
     tfrpn_proposal_cfg pcfg = {};
     const float* reg_host = nullptr;    // the caller's rpn_reg (any host memory): source of the row gather
@@ -223,11 +225,12 @@ struct Slot {
     char svc_err[256] = "";
     long long gathered = 0;            // rows of rpn_reg gathered for the step in flight
     bool pulled = false;               // the redo kernel counts the rows it pulls from the pinned tensor at L.pc
-    // incremental expansion of the compact bbox_deltas into the slot's own dense array
-    bool dense_clean = false;          // pin + L.d holds zeros except the rows listed in prev_idx
-    int pB = 0, pN = 0, pTP = 0;
+    float* labels_dst = nullptr;       // where the dense bbox_labels go: the slot's own array, or the caller's buffer
+    // incremental expansion of the sparse targets into the slot's own dense arrays
+    bool dense_clean = false;          // pin + L.d holds zeros except the rows listed in prev_idx, pin + L.l holds -1
+    int pB = 0, pN = 0, pTP = 0, pQ = 0;   //   except the entries coded in prev_lbl
     size_t p_off_d = 0;
-    std::vector<int32_t> prev_idx;
+    std::vector<int32_t> prev_idx, prev_lbl;
     struct Copy { void* dst; const void* src; size_t bytes; } copies[8 + 2 * MAX_CHUNKS];
     int n_copies = 0;
     void defer(void* d, const void* s, size_t b) { copies[n_copies].dst = d; copies[n_copies].src = s; copies[n_copies].bytes = b; ++n_copies; }
@@ -265,6 +268,7 @@ struct tfrpn_pipe {
     int gather_rows = 640;                            // rows of rpn_reg per image the two-phase transfer sends (adapts)
     bool gather_adapt = true;
     bool device_gather = false;                       // page-locked tensors: gather on the device instead of the host
+    bool sparse_labels = false;                       // bbox_labels returns as codes (scattered by host threads) instead of densely
 };
 
 namespace tfrpn {
@@ -287,8 +291,8 @@ static Layout make_layout(int B, int N, int G, int P) {
     L.pc = o;  o += 256;
     L.rf = o;  o += align256((size_t)B * 4);
     L.dense_end = o;
-    L.ci = o;  o += align256((size_t)B * COMPACT_MAX_POS * 4);
-    L.cd = o;  o += align256((size_t)B * COMPACT_MAX_POS * 16);
+    L.comp = o; o += align256((size_t)B * COMPACT_MAX_Q * 4) + align256((size_t)B * COMPACT_MAX_POS * 4) +
+                     align256((size_t)B * COMPACT_MAX_POS * 16);
     L.comp_end = o;
     L.ri = o;  o += align256((size_t)B * proposals_rank_cap() * 4);
     L.rn = o;  o += align256((size_t)B * 4);
@@ -345,26 +349,33 @@ static void gather_rows(tfrpn_pipe* p, Slot& s) {
     s.gathered = total.load();
 }
 
-// ---- host stage 2: the compact bbox_deltas rows into the dense (B,N,4) host array ----
-static void expand_deltas(tfrpn_pipe* p, Slot& s) {
+// ---- host stage 2: the sparse targets into the dense (B,N,4) bbox_deltas and (B,N) bbox_labels host arrays ----
+static void expand_targets(tfrpn_pipe* p, Slot& s, float* labels_dst) {
     const Step& st = s.step;
     float* own_dense = reinterpret_cast<float*>(s.pin + st.L.d);
     const bool own = st.dense_dst == own_dense;
-    const int B = st.B, N = st.N, TP = st.total_pos, pTP = s.pTP;
-    const bool reuse = own && s.dense_clean && s.pB == B && s.pN == N && s.p_off_d == st.L.d;
-    const int32_t* idx = reinterpret_cast<const int32_t*>(s.pin + st.L.ci);
-    const float* rows = reinterpret_cast<const float*>(s.pin + st.L.cd);
+    const int B = st.B, N = st.N, TP = st.total_pos, Q = st.Q, pTP = s.pTP, pQ = s.pQ;
+    // (a dense bbox_labels copy overwrites the slot's label array: the sparse bookkeeping restarts, pQ = 0 means "not -1-filled")
+    const bool reuse = own && s.dense_clean && s.pB == B && s.pN == N && s.p_off_d == st.L.d && (!st.sparse_labels || s.pQ > 0);
+    const int32_t* idx = reinterpret_cast<const int32_t*>(s.pin + st.ci);
+    const float* rows = reinterpret_cast<const float*>(s.pin + st.cd);
+    const int32_t* codes = reinterpret_cast<const int32_t*>(s.pin + st.cl);
     const int32_t* prev = reuse ? s.prev_idx.data() : nullptr;
+    const int32_t* prev_l = reuse ? s.prev_lbl.data() : nullptr;
     float* dense = st.dense_dst;
     constexpr int PIECE = 2;        // images per chunk
     p->pool->run((B + PIECE - 1) / PIECE, [&](int c) {
         const int b0 = c * PIECE, nb = (B - b0 < PIECE) ? B - b0 : PIECE;
         tfrpn_expand_targets_host(idx + (size_t)b0 * TP, rows + (size_t)b0 * TP * 4, nb, N, TP,
                                   prev ? prev + (size_t)b0 * pTP : nullptr, pTP, dense + (size_t)b0 * N * 4);
+        if (st.sparse_labels)
+            tfrpn_expand_labels_host(codes + (size_t)b0 * Q, nb, N, Q, prev_l ? prev_l + (size_t)b0 * pQ : nullptr, pQ,
+                                     labels_dst + (size_t)b0 * N);
     });
     if (own) {
         s.prev_idx.assign(idx, idx + (size_t)B * TP);
-        s.pB = B; s.pN = N; s.pTP = TP; s.p_off_d = st.L.d;
+        s.prev_lbl.assign(codes, codes + (size_t)B * Q);
+        s.pB = B; s.pN = N; s.pTP = TP; s.pQ = Q; s.p_off_d = st.L.d;
         s.dense_clean = true;
     }
 }
@@ -415,7 +426,7 @@ static int enqueue_tail(tfrpn_pipe* p, Slot& s) {
     // deltas travel in compact form; otherwise dense targets (acquired: one range; caller buffers: copied per chunk
     // by pipe_submit) and the small proposal results
     if (st.compact) {
-        const size_t lo = L.l, hi = L.cd + (size_t)B * st.total_pos * 16;
+        const size_t lo = !st.sparse_labels ? L.l : (st.do_p ? L.ob : L.rf), hi = st.cd + (size_t)B * st.total_pos * 16;
         TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin + lo, d + lo, hi - lo, cudaMemcpyDeviceToHost, s.s_out));
     } else if (st.acquired) {
         const size_t lo = st.do_t ? L.d : L.ob, hi = st.do_p ? L.dense_end : L.ob;
@@ -512,6 +523,8 @@ static int pipe_create(tfrpn_handle h, int depth, tfrpn_pipe** out) {
     tfrpn_pipe* p = new tfrpn_pipe();
     p->h = h;
     p->depth = depth;
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    const int local_ranks = lws && atoi(lws) > 0 ? atoi(lws) : 1;
     int threads = h->opts.host_threads;
     if (threads <= 0) {
         // default: half of this process's share of the cores it may run on, at most 8 -- the data loader and the
@@ -519,13 +532,15 @@ static int pipe_create(tfrpn_handle h, int depth, tfrpn_pipe** out) {
         int hw = (int)std::thread::hardware_concurrency();
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = CPU_COUNT(&set);
-        const char* lws = getenv("LOCAL_WORLD_SIZE");
-        const int ranks = lws && atoi(lws) > 0 ? atoi(lws) : 1;
-        const int share = hw / ranks;
+        const int share = hw / local_ranks;
         threads = share / 2 < 1 ? 1 : (share / 2 > 8 ? 8 : share / 2);
     }
     // TFRPN_PIPE_GATHER = host | device (default: host when the pool has >= 4 threads, else device)
     p->device_gather = h->opts.pipe_gather == 2 || (h->opts.pipe_gather == 0 && threads < 4);
+    // bbox_labels is -1 except <= total_pos + total_neg entries per image: as codes it is 65 KB instead of 2.2 MB per C2
+    // step, but the host then scatters 2 x 16 k floats per step into DRAM-resident arrays (~45 us on 8 threads), which
+    // costs a lone GPU more than the DMA it saves.  Worth it when many GPUs share the host's PCIe / memory bandwidth.
+    p->sparse_labels = h->opts.pipe_sparse_labels >= 0 ? h->opts.pipe_sparse_labels != 0 : local_ranks >= 4;
     if (depth == 1) threads = threads > 2 ? 2 : threads;   // a synchronous step only uses the pool for staging copies
     p->pool.reset(new HostPool(threads > 16 ? 16 : threads));
     p->gather_rows = initial_gather_rows(h);
@@ -593,9 +608,9 @@ static int slot_finish(tfrpn_pipe* p, Slot& s) {
         if (p->gather_adapt && redone * 16 > st.B && p->gather_rows < proposals_rank_cap())
             p->gather_rows = p->gather_rows + 128 > proposals_rank_cap() ? proposals_rank_cap() : p->gather_rows + 128;
     }
-    if (st.compact) {   // the retiring thread waits here anyway: it scatters the compact rows (worker pool)
+    if (st.compact) {   // the retiring thread waits here anyway: it scatters the sparse targets (worker pool)
         const auto t0 = std::chrono::steady_clock::now();
-        expand_deltas(p, s);
+        expand_targets(p, s, s.labels_dst);
         s.expand_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     for (int i = 0; i < s.n_copies; ++i) p->pool->copy(s.copies[i].dst, s.copies[i].src, s.copies[i].bytes);
@@ -686,7 +701,8 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     // zero outside the <= total_pos sampled positives, utils/train_utils.py:137) and the service thread scatters the
     // rows into the dense host array -- the slot's own (acquired: kept consistent incrementally) or the caller's.
     const bool several = p->depth > 1;   // a depth-1 pipeline is the synchronous step: chunked instead (below)
-    const bool compact = several && do_t && !h->opts.pipe_dense && a.tcfg->total_pos <= COMPACT_MAX_POS;
+    const bool compact = several && do_t && !h->opts.pipe_dense && a.tcfg->total_pos <= COMPACT_MAX_POS &&
+                         a.tcfg->total_pos + a.tcfg->total_neg <= COMPACT_MAX_Q;
     // The incremental expansion relies on the slot's dense deltas region still holding zeros plus the previous
     // step's rows.  Any step that is not an acquired compact step of the SAME layout may write into that region
     // (dense results, or the inputs / results of another (B,N,G,P) layout): forget the invariant.
@@ -703,7 +719,13 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     st = Step();
     st.do_t = do_t; st.do_p = do_p; st.acquired = acquired; st.compact = compact; st.two_phase = two_phase;
     st.B = B; st.N = N; st.G = G; st.P = P; st.GR = GR; st.total_pos = do_t ? a.tcfg->total_pos : 0;
+    st.sparse_labels = compact && p->sparse_labels;
+    st.Q = st.sparse_labels ? a.tcfg->total_pos + a.tcfg->total_neg : 0;
     st.L = L; st.anchors = a.anchors_dev;
+    st.cl = L.comp;                                              // packed with this step's quotas: one D2H range
+    st.ci = st.cl + (((size_t)B * st.Q * 4 + 15) & ~(size_t)15);
+    st.cd = st.ci + (((size_t)B * st.total_pos * 4 + 15) & ~(size_t)15);
+    s.labels_dst = acquired ? reinterpret_cast<float*>(pin + L.l) : a.labels;
     if (do_p) st.pcfg = *a.pcfg;
     st.reg_host = a.rpn_reg;
     // a caller's dense buffer (page-locked or not: the rows are written by host threads) is zeroed and filled in place
@@ -781,8 +803,10 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
             if (compact) {   // (compact => one chunk)
                 if (int rc = launch_targets(h, a.anchors_dev, reinterpret_cast<const float*>(d + L.gt),
                                             reinterpret_cast<const int32_t*>(d + L.gl), nb, N, G, &cc, nullptr,
-                                            reinterpret_cast<float*>(d + L.l), reinterpret_cast<int32_t*>(d + L.ci),
-                                            reinterpret_cast<float*>(d + L.cd), nullptr, p->s_tgt)) return rc;
+                                            st.sparse_labels ? nullptr : reinterpret_cast<float*>(d + L.l),
+                                            reinterpret_cast<int32_t*>(d + st.ci), reinterpret_cast<float*>(d + st.cd),
+                                            st.sparse_labels ? reinterpret_cast<int32_t*>(d + st.cl) : nullptr, nullptr,
+                                            p->s_tgt)) return rc;
             } else if (int rc = tfrpn_rpn_targets(h, a.anchors_dev, reinterpret_cast<const float*>(d + L.gt) + (size_t)lo * G * 4,
                                            reinterpret_cast<const int32_t*>(d + L.gl) + (size_t)lo * G, nb, N, G, &cc,
                                            reinterpret_cast<float*>(d + L.d) + (size_t)lo * N * 4,
@@ -798,11 +822,11 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
         }
     }
     // bytes of the result copy enqueue_tail makes
-    if (compact) p->last_d2h += (long long)(L.cd + (size_t)B * a.tcfg->total_pos * 16 - L.l);
+    if (compact && !acquired && !st.sparse_labels) s.defer(a.labels, pin + L.l, (size_t)B * N * 4);
+    if (compact) p->last_d2h += (long long)(st.cd + (size_t)B * a.tcfg->total_pos * 16 - (!st.sparse_labels ? L.l : (do_p ? L.ob : L.rf)));
     else if (acquired) p->last_d2h += (long long)((do_p ? L.dense_end : L.ob) - (do_t ? L.d : L.ob));
     else if (do_p) p->last_d2h += (long long)(L.dense_end - L.ob);
     if (!acquired) {   // results that land in the slot's pinned block are copied out when the step is retired
-        if (compact) s.defer(a.labels, pin + L.l, (size_t)B * N * 4);
         if (do_p) {
             s.defer(a.out_boxes, pin + L.ob, (size_t)B * P * 16);
             s.defer(a.out_scores, pin + L.os, (size_t)B * P * 4);

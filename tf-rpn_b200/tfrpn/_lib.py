@@ -82,6 +82,8 @@ PROTOTYPES = {
     "tfrpn_nms": (I, [P, P, P, I, I, C.POINTER(NmsCfg), P, P, P, P, P, P]),
     "tfrpn_proposals": (I, [P, P, P, P, I, I, C.POINTER(ProposalCfg), P, P, P, P, P]),
     "tfrpn_proposals_anchor_cfg": (I, [P, P, P, C.POINTER(AnchorCfg), I, C.POINTER(ProposalCfg), P, P, P, P, P]),
+    "tfrpn_rpn_targets_sparse": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P, P]),
+    "tfrpn_expand_labels_host": (I, [P, I, I, I, P, I, P]),
     "tfrpn_rpn_targets_host": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P]),
     "tfrpn_proposals_host": (I, [P, P, P, P, I, I, C.POINTER(ProposalCfg), P, P, P, P, P]),
     "tfrpn_rpn_step_host": (I, [P, P, P, P, I, I, I, C.POINTER(TargetCfg), P, P, P, P, C.POINTER(ProposalCfg), P, P, P, P, P]),

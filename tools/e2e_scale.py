@@ -20,14 +20,14 @@ rng = np.random.default_rng(1 + rank)
 gtb, gtl = synthetic.gt_batch(rng, B, G)
 reg, cls = synthetic.head_outputs(rng, B, 31, 31, 9)
 modes = [("auto", {}),
-         ("device gather", {"TFRPN_PIPE_GATHER": "device"}),
-         ("host gather, 2 threads", {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": "2"}),
-         ("host gather, 3 threads", {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": "3"}),
-         ("host gather, 4 threads", {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": "4"}),
-         ("dense input, compact output", {"TFRPN_PIPE_DENSE_IN": "1"}),
-         ("targets only (auto)", {"_mode": "targets"}),
-         ("proposals only, device gather", {"TFRPN_PIPE_GATHER": "device", "_mode": "proposals"}),
-         ("proposals only, host gather 3", {"TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": "3", "_mode": "proposals"})]
+         ("dense labels, device gather", {"TFRPN_PIPE_SPARSE_LABELS": "0", "TFRPN_PIPE_GATHER": "device"}),
+         ("sparse labels, device gather", {"TFRPN_PIPE_SPARSE_LABELS": "1", "TFRPN_PIPE_GATHER": "device"}),
+         ("sparse labels, host gather 3 thr", {"TFRPN_PIPE_SPARSE_LABELS": "1", "TFRPN_PIPE_GATHER": "host", "TFRPN_HOST_THREADS": "3"}),
+         ("sparse labels, device gather, 1 thr", {"TFRPN_PIPE_SPARSE_LABELS": "1", "TFRPN_PIPE_GATHER": "device", "TFRPN_HOST_THREADS": "1"}),
+         ("targets only, dense labels", {"TFRPN_PIPE_SPARSE_LABELS": "0", "_mode": "targets"}),
+         ("targets only, sparse labels", {"TFRPN_PIPE_SPARSE_LABELS": "1", "_mode": "targets"})]
+if len(sys.argv) > 2:
+    modes = [m for m in modes if any(k in m[0] for k in sys.argv[2].split(","))]
 def barrier():
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
