@@ -125,6 +125,13 @@ def test_acquired_sparse_labels(cuda_device):
     run_acquired(cuda_device, 6, 9, 2, 6, {"TFRPN_PIPE_SPARSE_LABELS": 0})
 
 
+def test_acquired_device_side_expansion(cuda_device):
+    """TFRPN_PIPE_EXPAND=device: a kernel keeps the slot's dense bbox_deltas array (page-locked host memory) up to date --
+    zeroes the previous step's rows, writes this step's -- and the host scatters nothing (slots reused: depth 2)"""
+    run_acquired(cuda_device, 64, 50, 4, 9, {"TFRPN_PIPE_EXPAND": "device"})
+    run_acquired(cuda_device, 6, 9, 2, 7, {"TFRPN_PIPE_EXPAND": "device", "TFRPN_PIPE_GATHER": "device", "TFRPN_HOST_THREADS": 1})
+
+
 def test_acquired_dense_input_switch_equals_two_phase(cuda_device):
     run_acquired(cuda_device, 7, 5, 3, 4, {"TFRPN_PIPE_DENSE_IN": 1})
     run_acquired(cuda_device, 7, 5, 3, 4, {"TFRPN_PIPE_DENSE": 1})

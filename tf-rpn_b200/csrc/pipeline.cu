@@ -49,6 +49,8 @@ size_t targets_workspace_bytes(int B, int N, int G);  // targets.cu
 int launch_targets(tfrpn_handle h, const float* anchors, const float* gt_boxes, const int32_t* gt_labels, int B, int N,
                    int G, const tfrpn_target_cfg* cfg, float* deltas, float* labels, int32_t* pos_idx,
                    float* pos_deltas, int32_t* lbl_code, const tfrpn_target_debug* dbg, tfrpn_stream s);
+int scatter_rows_to_host_enqueue(int32_t* prev_idx, int prev_tp, const int32_t* idx, const float* rows, int tp, int B, int N,
+                                 float* dense_host_dev_alias, int stride_prev, cudaStream_t st);
 int proposals_enqueue(tfrpn_handle h, const float* rpn_reg, const float* rpn_cls, const float* anchors, int B, int N,
                       const tfrpn_proposal_cfg* cfg, float* out_boxes, float* out_scores, int32_t* valid,
                       int32_t* keep_idx_or_null, unsigned long long* rows_fetched_or_null, cudaStream_t st);   // proposals.cu
@@ -189,12 +191,14 @@ struct Layout {
     size_t gt, gl, cls, small_end, reg, in_end; // inputs: the small ones first, the head's regression output last
     size_t d, l, ob, os, v, k, pc, rf, dense_end;   // results (pc: rows of rpn_reg pulled; rf: redo flags)
     size_t comp, comp_end;                      // sparse targets (label codes, row indices, rows: packed at submit)
+    size_t pci;                                 // device side: row indices the slot's dense host array still holds (device expansion)
     size_t ri, rn, rm, rank_end, rc, mk, total; // two-phase: rank indices / counts / more flags (D2H), compact rows (H2D), NMS matrix
 };
 
 // everything the later stages of the step in flight need (filled by pipe_submit, read by the service thread)
 struct Step {
     bool do_t = false, do_p = false, acquired = false, compact = false, two_phase = false, sparse_labels = false;
+    bool device_expand = false;         // the dense bbox_deltas host array is kept up to date by a kernel (no host scatter)
     bool reg_pinned = false;            // the caller's rpn_reg is page-locked: the device can read it (redo pulls rows)
     bool device_gather = false;         // the rows are gathered by a kernel reading the page-locked tensor (no host stage)
     int B = 0, N = 0, G = 0, P = 0, GR = 0, total_pos = 0, Q = 0;
@@ -231,6 +235,9 @@ struct Slot {
     int pB = 0, pN = 0, pTP = 0, pQ = 0;   //   except the entries coded in prev_lbl
     size_t p_off_d = 0;
     std::vector<int32_t> prev_idx, prev_lbl;
+    bool dev_clean = false;            // ... or the same invariant with the row list kept on the device (L.pci): device expansion
+    int dB = 0, dN = 0;
+    size_t d_off_d = 0;
     struct Copy { void* dst; const void* src; size_t bytes; } copies[8 + 2 * MAX_CHUNKS];
     int n_copies = 0;
     void defer(void* d, const void* s, size_t b) { copies[n_copies].dst = d; copies[n_copies].src = s; copies[n_copies].bytes = b; ++n_copies; }
@@ -269,6 +276,7 @@ struct tfrpn_pipe {
     bool gather_adapt = true;
     bool device_gather = false;                       // page-locked tensors: gather on the device instead of the host
     bool sparse_labels = false;                       // bbox_labels returns as codes (scattered by host threads) instead of densely
+    bool device_expand = false;                       // acquired slots: a kernel scatters the bbox_deltas rows into the pinned array
 };
 
 namespace tfrpn {
@@ -294,6 +302,7 @@ static Layout make_layout(int B, int N, int G, int P) {
     L.comp = o; o += align256((size_t)B * COMPACT_MAX_Q * 4) + align256((size_t)B * COMPACT_MAX_POS * 4) +
                      align256((size_t)B * COMPACT_MAX_POS * 16);
     L.comp_end = o;
+    L.pci = o; o += align256((size_t)B * COMPACT_MAX_POS * 4);
     L.ri = o;  o += align256((size_t)B * proposals_rank_cap() * 4);
     L.rn = o;  o += align256((size_t)B * 4);
     L.rm = o;  o += align256((size_t)B * 4);
@@ -426,7 +435,8 @@ static int enqueue_tail(tfrpn_pipe* p, Slot& s) {
     // deltas travel in compact form; otherwise dense targets (acquired: one range; caller buffers: copied per chunk
     // by pipe_submit) and the small proposal results
     if (st.compact) {
-        const size_t lo = !st.sparse_labels ? L.l : (st.do_p ? L.ob : L.rf), hi = st.cd + (size_t)B * st.total_pos * 16;
+        const size_t lo = !st.sparse_labels ? L.l : (st.do_p ? L.ob : L.rf);
+        const size_t hi = st.device_expand ? L.dense_end : st.cd + (size_t)B * st.total_pos * 16;
         TFRPN_CHECK_CUDA(cudaMemcpyAsync(pin + lo, d + lo, hi - lo, cudaMemcpyDeviceToHost, s.s_out));
     } else if (st.acquired) {
         const size_t lo = st.do_t ? L.d : L.ob, hi = st.do_p ? L.dense_end : L.ob;
@@ -540,7 +550,14 @@ static int pipe_create(tfrpn_handle h, int depth, tfrpn_pipe** out) {
     // bbox_labels is -1 except <= total_pos + total_neg entries per image: as codes it is 65 KB instead of 2.2 MB per C2
     // step, but the host then scatters 2 x 16 k floats per step into DRAM-resident arrays (~45 us on 8 threads), which
     // costs a lone GPU more than the DMA it saves.  Worth it when many GPUs share the host's PCIe / memory bandwidth.
-    p->sparse_labels = h->opts.pipe_sparse_labels >= 0 ? h->opts.pipe_sparse_labels != 0 : local_ranks >= 4;
+    p->sparse_labels = h->opts.pipe_sparse_labels > 0;
+    (void)local_ranks;
+    // TFRPN_PIPE_EXPAND = host (default) | device: who scatters the compact bbox_deltas rows into the dense host array.
+    // Measured (profiles/r2_scale/e2e_policies_8gpu.txt): a lone GPU loses with the device variant (its 2 x 8 k posted
+    // 16-byte writes per step share the PCIe small-request path: targets-only 96 instead of 56 us per step), and with
+    // 8 ranks on one host every variant ends at ~250 us per half-step -- that box moves ~90 GB/s between all GPUs and
+    // host memory, whoever issues the transfers -- so the host scatter stays the default.
+    p->device_expand = h->opts.pipe_expand == 2;
     if (depth == 1) threads = threads > 2 ? 2 : threads;   // a synchronous step only uses the pool for staging copies
     p->pool.reset(new HostPool(threads > 16 ? 16 : threads));
     p->gather_rows = initial_gather_rows(h);
@@ -608,7 +625,7 @@ static int slot_finish(tfrpn_pipe* p, Slot& s) {
         if (p->gather_adapt && redone * 16 > st.B && p->gather_rows < proposals_rank_cap())
             p->gather_rows = p->gather_rows + 128 > proposals_rank_cap() ? proposals_rank_cap() : p->gather_rows + 128;
     }
-    if (st.compact) {   // the retiring thread waits here anyway: it scatters the sparse targets (worker pool)
+    if (st.compact && !st.device_expand) {   // the retiring thread waits here anyway: it scatters the sparse targets (worker pool)
         const auto t0 = std::chrono::steady_clock::now();
         expand_targets(p, s, s.labels_dst);
         s.expand_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -706,7 +723,9 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     // The incremental expansion relies on the slot's dense deltas region still holding zeros plus the previous
     // step's rows.  Any step that is not an acquired compact step of the SAME layout may write into that region
     // (dense results, or the inputs / results of another (B,N,G,P) layout): forget the invariant.
-    if (!(compact && acquired && s.pB == B && s.pN == N && s.p_off_d == L.d)) s.dense_clean = false;
+    const bool device_expand = compact && acquired && p->device_expand && !p->sparse_labels;
+    if (!(compact && acquired && !device_expand && s.pB == B && s.pN == N && s.p_off_d == L.d)) s.dense_clean = false;
+    if (!(device_expand && s.dB == B && s.dN == N && s.d_off_d == L.d)) s.dev_clean = false;
     // Two-phase proposals (see the header of this file).  TFRPN_PIPE_DENSE_IN=1 copies the whole rpn_reg tensor.
     const bool two_phase = several && do_p && !h->opts.pipe_dense_in && proposals_two_phase_applies(B, N, a.pcfg);
     // A synchronous step is chunked over images so that copies overlap its own kernels; with several steps in
@@ -719,6 +738,7 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     st = Step();
     st.do_t = do_t; st.do_p = do_p; st.acquired = acquired; st.compact = compact; st.two_phase = two_phase;
     st.B = B; st.N = N; st.G = G; st.P = P; st.GR = GR; st.total_pos = do_t ? a.tcfg->total_pos : 0;
+    st.device_expand = device_expand;
     st.sparse_labels = compact && p->sparse_labels;
     st.Q = st.sparse_labels ? a.tcfg->total_pos + a.tcfg->total_neg : 0;
     st.L = L; st.anchors = a.anchors_dev;
@@ -807,6 +827,18 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
                                             reinterpret_cast<int32_t*>(d + st.ci), reinterpret_cast<float*>(d + st.cd),
                                             st.sparse_labels ? reinterpret_cast<int32_t*>(d + st.cl) : nullptr, nullptr,
                                             p->s_tgt)) return rc;
+                if (device_expand) {
+                    float* dense = reinterpret_cast<float*>(pin + L.d);   // (UVA: a cudaHostAlloc pointer is its own device alias)
+                    int32_t* pci = reinterpret_cast<int32_t*>(d + L.pci);
+                    if (!s.dev_clean) {   // first use of this layout: the whole array is zeroed once, over PCIe
+                        TFRPN_CHECK_CUDA(cudaMemsetAsync(dense, 0, (size_t)B * N * 16, p->s_tgt));
+                        TFRPN_CHECK_CUDA(cudaMemsetAsync(pci, 0xFF, (size_t)B * COMPACT_MAX_POS * 4, p->s_tgt));
+                    }
+                    if (int rc = scatter_rows_to_host_enqueue(pci, COMPACT_MAX_POS, reinterpret_cast<int32_t*>(d + st.ci),
+                                                              reinterpret_cast<float*>(d + st.cd), a.tcfg->total_pos, B, N, dense,
+                                                              COMPACT_MAX_POS, p->s_tgt)) return rc;
+                    s.dev_clean = true; s.dB = B; s.dN = N; s.d_off_d = L.d;
+                }
             } else if (int rc = tfrpn_rpn_targets(h, a.anchors_dev, reinterpret_cast<const float*>(d + L.gt) + (size_t)lo * G * 4,
                                            reinterpret_cast<const int32_t*>(d + L.gl) + (size_t)lo * G, nb, N, G, &cc,
                                            reinterpret_cast<float*>(d + L.d) + (size_t)lo * N * 4,
@@ -823,7 +855,8 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     }
     // bytes of the result copy enqueue_tail makes
     if (compact && !acquired && !st.sparse_labels) s.defer(a.labels, pin + L.l, (size_t)B * N * 4);
-    if (compact) p->last_d2h += (long long)(st.cd + (size_t)B * a.tcfg->total_pos * 16 - (!st.sparse_labels ? L.l : (do_p ? L.ob : L.rf)));
+    if (compact) p->last_d2h += (long long)((device_expand ? L.dense_end + (size_t)2 * B * a.tcfg->total_pos * 16 : st.cd + (size_t)B * a.tcfg->total_pos * 16) -
+                                            (!st.sparse_labels ? L.l : (do_p ? L.ob : L.rf)));   // (device expansion: + the rows written over PCIe)
     else if (acquired) p->last_d2h += (long long)((do_p ? L.dense_end : L.ob) - (do_t ? L.d : L.ob));
     else if (do_p) p->last_d2h += (long long)(L.dense_end - L.ob);
     if (!acquired) {   // results that land in the slot's pinned block are copied out when the step is retired
