@@ -22,7 +22,7 @@ def run(n):
         tfrpn.generate_proposals(reg, cls, anchors, hp)
 run(6); torch.cuda.synchronize()
 _lib.check(lib.tfrpn_profile_enable(h, 1)); run(60)
-for kid in range(4):
+for kid in range(_lib.KERNEL_IDS):
     tot, n = C.c_double(), C.c_int()
     _lib.check(lib.tfrpn_profile_read(h, kid, C.byref(tot), C.byref(n)))
     if n.value: print("%-28s %7.2f us  (n=%d)" % (lib.tfrpn_kernel_name(kid).decode(), 1e3 * tot.value / n.value, n.value))
