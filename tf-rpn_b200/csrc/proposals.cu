@@ -558,7 +558,7 @@ struct ClShared {
     unsigned int wtot[32], wtot2[32];
     unsigned int digit, excl, bin_count, total;
     unsigned int count;                // compaction cursor, then the batch's entry count
-    unsigned int valid_all[CL_MAX];    // per-CTA counts of the entries above the score threshold
+    unsigned int valid_all[CL_MAX];    // [0]: this CTA's count of entries above the score threshold (peers read it after the first barrier)
     unsigned int dead_all[2][CL_MAX][4];  // [round parity][CTA]: "suppressed by the kept list" bits
     unsigned int dead_w[4];            // the bits found inside this CTA
     int nk;
@@ -696,17 +696,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
         my_valid = __reduce_add_sync(0xffffffffu, my_valid);
         if (lane == 0) sh.wtot[warp] = my_valid;
         __syncthreads();
-        if (tid < CL) {
+        if (tid == 0) {   // this CTA's count stays LOCAL until the barrier: a peer may not have started yet
             unsigned int tot = 0;
             for (int w = 0; w < WARPS; ++w) tot += sh.wtot[w];
-            cl_peer<CL>(sh.valid_all + crank, (unsigned)tid)[0] = tot;
+            sh.valid_all[0] = tot;
         }
     }
     // (every CTA of the cluster must be running before the first remote shared-memory access)
     cl_sync<CL>();
     if (p.use_sthr) {
         M = 0;
-        for (int q = 0; q < CL; ++q) M += (int)sh.valid_all[q];
+        for (int q = 0; q < CL; ++q) M += (int)*cl_peer<CL>(&sh.valid_all[0], (unsigned)q);
     }
     int K = min(p.k, M);                    // ranks that may be consumed
     bool cut = false;                       // presorted: the launch cannot serve every rank of the batch
@@ -1263,6 +1263,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) nms_sweep_kernel(const __grid_c
                 keptw[q] = __ballot_sync(0xffffffffu, kept);
                 before += __popc(Kp[q]);
             }
+            __syncwarp();   // every lane has read dead_s[] above
             if (lane < 4) {
                 kw[w0 + lane] = lane == 0 ? keptw[0] : lane == 1 ? keptw[1] : lane == 2 ? keptw[2] : keptw[3];
                 dead_s[lane] = 0u;
