@@ -480,7 +480,7 @@ def run_ours(args):
         # launch occupies (one CTA, or one cluster of CTAs, per image)
         roofline["note"] = ("not HBM-bound: per-image select / sort / sequential greedy NMS; see `work` for the "
                             "issue-capacity view (warp instructions from the committed ncu capture)")
-        cl = 1 if dominant != "proposal_cluster_kernel" else (8 if B <= 32 else 2)     # proposals.cu: pick_cluster
+        cl = 1 if dominant != "proposal_cluster_kernel" else (8 if B <= 8 else 2)      # proposals.cu: pick_cluster
         sms_used = min(148, B * cl)
         work = {"us_per_image_batch": dom_us, "images": B, "us_per_image": dom_us / B, "ctas": B * cl, "sms_used": sms_used}
         if dominant.startswith("proposal") and rpn:

@@ -197,8 +197,10 @@ M = {"TFRPN_NMS_PATH": "matrix"}
 
 
 @pytest.mark.parametrize("env", [{}, M, dict(M, TFRPN_NMS_ROWS=64), dict(M, TFRPN_NMS_ROWS=256), dict(M, TFRPN_NMS_ROWS=1024),
-                                 {"TFRPN_PROP_CLUSTER": 0}, dict(M, TFRPN_PROP_CLUSTER=18)],
-                         ids=["lazy", "matrix", "matrix64_redo", "matrix256_redo", "matrix1024", "lazy_one_cta", "matrix_rank_8x256"])
+                                 {"TFRPN_PROP_CLUSTER": 0}, {"TFRPN_PROP_CLUSTER": 12}, {"TFRPN_PROP_CLUSTER": 18},
+                                 {"TFRPN_PROP_CLUSTER": 14}, {"TFRPN_PROP_CLUSTER": 1}, dict(M, TFRPN_PROP_CLUSTER=18)],
+                         ids=["lazy", "matrix", "matrix64_redo", "matrix256_redo", "matrix1024", "lazy_one_cta", "lazy_2x512",
+                              "lazy_8x256", "lazy_4x256", "lazy_1x1024", "matrix_rank_8x256"])
 def test_nms_paths_agree_with_oracle(T, env):
     """the lazy NMS kernels (default) and the matrix NMS (rank launch + mask + sweep), also with too few rows (every
     image redone by the lazy kernel): the same keep lists as the oracle"""

@@ -59,7 +59,7 @@ int ensure_kernel_attributes(int device) {
 
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
+    return (e && *e) ? atoi(e) : dflt;   // (an empty value means "not set")
 }
 
 int grow_buffer(char** buf, size_t* have, size_t want, cudaStream_t s, bool pinned) {

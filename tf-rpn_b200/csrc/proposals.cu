@@ -1324,10 +1324,14 @@ int set_attributes_proposals() {
     return 0;
 }
 
-// Shape of the proposal stage for a batch of B images (measured, profiles/r2c_prop_shapes.txt): total threads
-// around 64 k is the sweet spot -- B <= 32: 8 CTAs x 256 threads per image; B <= 95: 2 CTAs x 512; larger batches
-// fill the GPU with one 1024-thread CTA per image (proposal_kernel).  TFRPN_PROP_CLUSTER = 10 * t + cl forces a
-// shape (A/B switch): cl = 0 one-CTA kernel, 1 / 2 / 4 / 8 CTAs per image; t selects the threads per CTA.
+// Shape of the proposal stage for a batch of B images.  Measured (profiles/r2l_prop_shapes.txt): alone on the GPU the
+// cluster kernels are faster (C2, B = 64: 2 x 512 = 41 us against 48.8 us; C1, B = 1: 8 x 256 = 28 us against 46 us),
+// but they execute more instructions (16.4 M against 13.8 M warp instructions at C2) and hold twice the SMs, so as soon
+// as the batch alone can fill the GPU -- and with the target kernels and other steps running beside it -- the one-CTA
+// kernel gives more images/s AND the lower step latency (bench.py at C2: 1.42 M images/s, p50 67.6 us against 1.34 M,
+// 71.7 us with 2 x 512; C4, B = 32: 196 k against 173 k with 8 x 256).  Hence: B <= 8 -> 8 CTAs x 256 threads per
+// image, larger batches -> one 1024-thread CTA per image.  TFRPN_PROP_CLUSTER = 10 * t + cl forces a shape (A/B
+// switch): cl = 0 one-CTA kernel, 1 / 2 / 4 / 8 CTAs per image; t selects the threads per CTA.
 static void pick_cluster(tfrpn_handle h, int B, int& cl, int& threads) {
     const int v = h->opts.prop_cluster;
     if (v >= 0) {
@@ -1337,8 +1341,7 @@ static void pick_cluster(tfrpn_handle h, int B, int& cl, int& threads) {
         threads = cl == 1 ? 1024 : cl == 2 ? (t == 1 ? 512 : 1024) : cl == 4 ? (t == 1 ? 256 : 512) : (t == 2 ? 512 : 256);
         return;
     }
-    if (B <= 32) { cl = 8; threads = 256; }
-    else if (B <= 95) { cl = 2; threads = 512; }
+    if (B <= 8) { cl = 8; threads = 256; }
     else { cl = 0; threads = 1024; }
 }
 
