@@ -184,6 +184,7 @@ extern "C" int tfrpn_create(tfrpn_handle* out, int device) {
     h->opts.pipe_trace = getenv("TFRPN_PIPE_TRACE") != nullptr;
     h->opts.pipe_gather_rows = env_int("TFRPN_PIPE_GATHER_ROWS", 0);
     h->opts.host_threads = env_int("TFRPN_HOST_THREADS", 0);
+    h->opts.svc_threads = env_int("TFRPN_SVC_THREADS", 0);
     h->opts.pipe_sparse_labels = env_int("TFRPN_PIPE_SPARSE_LABELS", -1);
     if (const char* g = getenv("TFRPN_PIPE_EXPAND")) h->opts.pipe_expand = !strcmp(g, "host") ? 1 : (!strcmp(g, "device") ? 2 : 0);
     if (const char* g = getenv("TFRPN_NMS_PATH")) h->opts.nms_lazy = strcmp(g, "matrix") != 0;

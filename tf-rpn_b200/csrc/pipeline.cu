@@ -260,8 +260,9 @@ struct tfrpn_pipe {
     bool trace = false;             // TFRPN_PIPE_TRACE=1 (read when the handle was created)
     cudaEvent_t ev_base = nullptr;  // time origin of the trace
     std::unique_ptr<HostPool> pool;
-    // service thread
-    std::thread svc;
+    // service threads (jobs of different slots are independent; each job stays with the thread that took it)
+    std::thread svc[2];
+    int n_svc = 0;
     std::mutex svc_mu;
     std::condition_variable svc_cv;
     std::deque<StageJob> svc_inbox;
@@ -463,7 +464,11 @@ static void service_loop(tfrpn_pipe* p) {
             std::unique_lock<std::mutex> lk(p->svc_mu);
             if (pending.empty()) p->svc_cv.wait(lk, [&] { return p->svc_stop || !p->svc_inbox.empty(); });
             if (p->svc_stop && pending.empty() && p->svc_inbox.empty()) return;
-            while (!p->svc_inbox.empty()) { pending.push_back(p->svc_inbox.front()); p->svc_inbox.pop_front(); }
+            // (with two threads a thread that already holds a job leaves the inbox to the other one)
+            while (!p->svc_inbox.empty() && (p->n_svc == 1 || pending.empty())) {
+                pending.push_back(p->svc_inbox.front());
+                p->svc_inbox.pop_front();
+            }
         }
         bool progress = false;
         for (size_t i = 0; i < pending.size();) {
@@ -496,13 +501,13 @@ void pipe_destroy(tfrpn_pipe* p) {
     if (!p) return;
     DeviceGuard guard(p->h->device);
     for (int i = 0; i < p->depth; ++i) slot_finish(p, p->slots[i]);
-    if (p->svc.joinable()) {
+    if (p->n_svc > 0) {
         {
             std::lock_guard<std::mutex> lk(p->svc_mu);
             p->svc_stop = true;
         }
         p->svc_cv.notify_all();
-        p->svc.join();
+        for (int i = 0; i < p->n_svc; ++i) if (p->svc[i].joinable()) p->svc[i].join();
     }
     for (int i = 0; i < p->depth; ++i)
         for (cudaStream_t s : {p->slots[i].s_in, p->slots[i].s_prop, p->slots[i].s_out})
@@ -583,7 +588,12 @@ static int pipe_create(tfrpn_handle h, int depth, tfrpn_pipe** out) {
             for (cudaEvent_t& ev : p->slots[i].tr) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     }
     if (e != cudaSuccess) { pipe_destroy(p); return cuda_fail(e, "pipeline_create"); }
-    if (depth > 1) p->svc = std::thread(service_loop, p);
+    if (depth > 1) {
+        // TFRPN_SVC_THREADS=2: one thread gathers while the other enqueues the tail of its step.  Measured at C2: no
+        // consistent gain (the worker pool, i.e. host memory latency, is the limit: 570-770 k images/s either way).
+        p->n_svc = h->opts.svc_threads >= 2 ? 2 : 1;
+        for (int i = 0; i < p->n_svc; ++i) p->svc[i] = std::thread(service_loop, p);
+    }
     *out = p;
     return 0;
 }

@@ -77,11 +77,22 @@ class HostPipeline:
         self._pipe = pipe
         self._views = {}
         self._keep = {}
+        # per-step ctypes objects are reused: building them costs more than the C call they are passed to
+        self._sb = _lib.StepBuffers()
+        self._sb_ref = C.byref(self._sb)
+        self._tcfg = train_utils._target_cfg(hyper_params, 0, 0, 0)
+        self._tcfg_ref = C.byref(self._tcfg)
+        self._pcfg_ref = C.byref(self.pcfg)
+        self._ticket = C.c_int64()
+        self._ticket_ref = C.byref(self._ticket)
+        self._anchors_ptr = self.anchors.data_ptr()
 
     def acquire(self, batch, max_gt):
         B, G, N, P = int(batch), int(max_gt), self.N, self.P
-        sb = _lib.StepBuffers()
-        _lib.check(self._lib.tfrpn_pipeline_acquire(self._pipe, B, N, G, P, C.byref(sb)))
+        sb = self._sb
+        rc = self._lib.tfrpn_pipeline_acquire(self._pipe, B, N, G, P, self._sb_ref)
+        if rc:
+            _lib.check(rc)
         key = (sb.gt_boxes, B, G)
         v = self._views.get(key)
         if v is None:
@@ -99,12 +110,16 @@ class HostPipeline:
         return v
 
     def submit(self, targets=True, proposals=True, seed=None, offset=None, image_offset=0):
-        tcfg = train_utils._target_cfg(self.hp, seed, offset, image_offset) if targets else None
-        t = C.c_int64()
-        _lib.check(self._lib.tfrpn_pipeline_submit_acquired(
-            self._pipe, self.anchors.data_ptr(), C.byref(tcfg) if targets else None,
-            C.byref(self.pcfg) if proposals else None, C.byref(t)))
-        return t.value
+        if targets:   # only the RNG fields change from step to step (utils/train_utils.py:50-65 has no state to carry)
+            tcfg = self._tcfg
+            tcfg.seed = int(self.hp.get("seed", 0) if seed is None else seed)
+            tcfg.offset = next(train_utils._auto_offset) if offset is None else int(offset)
+            tcfg.image_offset = int(image_offset)
+        rc = self._lib.tfrpn_pipeline_submit_acquired(self._pipe, self._anchors_ptr, self._tcfg_ref if targets else None,
+                                                      self._pcfg_ref if proposals else None, self._ticket_ref)
+        if rc:
+            _lib.check(rc)
+        return self._ticket.value
 
     def submit_arrays(self, gt_boxes=None, gt_labels=None, rpn_reg=None, rpn_cls=None, out=None, seed=None, offset=None,
                       image_offset=0):
@@ -149,7 +164,9 @@ class HostPipeline:
         return t.value, out
 
     def wait(self, ticket):
-        _lib.check(self._lib.tfrpn_pipeline_wait(self._pipe, int(ticket)))
+        rc = self._lib.tfrpn_pipeline_wait(self._pipe, ticket)
+        if rc:
+            _lib.check(rc)
 
     def last_copy_bytes(self):
         """(H2D, D2H) bytes of the last submitted step.  The target tensors cross PCIe in compact form (labels as
