@@ -328,46 +328,55 @@ def _nms_iou_vs(box, sel):
 def combined_non_max_suppression(boxes, scores, max_output_size_per_class, max_total_size,
                                  iou_threshold=0.5, score_threshold=float("-inf"),
                                  pad_per_class=False, clip_boxes=True, return_indices=False):
-    """tf.image.combined_non_max_suppression for q = num_classes = 1 [TF-internal].
+    """tf.image.combined_non_max_suppression [TF-internal].
 
-    boxes (B,K,1,4), scores (B,K,1).  Greedy in score order (equal scores: lower index
-    first -- TF's heap order for ties is unspecified; this is the documented rule), suppress
-    iff IoU > iou_threshold (strict), stop at max_output_size_per_class; truncate to
-    max_total_size; zero pad; clip OUTPUT boxes to [0,1].  Also returns the kept indices
-    (-1 padded) when ``return_indices`` (TF returns none).
+    boxes (B,K,q,4) with q = 1 (boxes shared by the classes) or q = C, scores (B,K,C).  Per image and class:
+    greedy in score order (equal scores: lower index first -- TF's heap order for ties is unspecified; this is
+    the documented rule), suppress iff IoU > iou_threshold (strict), stop at max_output_size_per_class.  The
+    per-class results are then merged by score (descending; TF uses an unstable std::sort, the documented rule
+    here: equal scores -> lower class id first, then the class's own order) and truncated to max_total_size.
+    Output rows: max_total_size, or with pad_per_class min(max_total_size, max_output_size_per_class * C); zero
+    padded; OUTPUT boxes clipped to [0,1] when clip_boxes.  nmsed_classes holds the class ids as floats.  Also
+    returns the kept box indices (-1 padded) when ``return_indices`` (TF returns none).
     """
     boxes = np.asarray(boxes, F32)
     scores = np.asarray(scores, F32)
-    assert boxes.ndim == 4 and boxes.shape[2] == 1 and scores.shape[2] == 1
-    B, K = scores.shape[:2]
+    assert boxes.ndim == 4 and scores.ndim == 3
+    B, K, C = scores.shape
+    q = boxes.shape[2]
+    assert q in (1, C), "boxes must be (B,K,1,4) or (B,K,C,4)"
     per_class = int(max_output_size_per_class)
     total = int(max_total_size)
-    out_n = total if not pad_per_class else min(total, per_class)
+    out_n = total if not pad_per_class else min(total, per_class * C)
     thr = F32(iou_threshold)
     sthr = F32(score_threshold)
     nb = np.zeros((B, out_n, 4), F32); ns = np.zeros((B, out_n), F32)
     nc = np.zeros((B, out_n), F32); nv = np.zeros((B,), np.int32)
     ni = np.full((B, out_n), -1, np.int32)
     for b in range(B):
-        bx = boxes[b, :, 0, :]
-        sc = scores[b, :, 0]
-        order = np.argsort(-sc.astype(np.float64), kind="stable")
-        order = order[sc[order] > sthr]
-        sel = []
-        for i in order:
-            if len(sel) >= per_class:
-                break
-            if sel and np.any(_nms_iou_vs(bx[i], bx[sel]) > thr):
-                continue
-            sel.append(int(i))
-        sel = sel[:out_n]
-        n = len(sel)
-        nv[b] = n
-        if n:
-            kept = bx[sel]
-            nb[b, :n] = np.clip(kept, F32(0), F32(1)) if clip_boxes else kept
-            ns[b, :n] = sc[sel]
-            ni[b, :n] = sel
+        cand = []                                   # (score, class, position in the class's keep list, box index)
+        for c in range(C):
+            bx = boxes[b, :, c if q > 1 else 0, :]
+            sc = scores[b, :, c]
+            order = np.argsort(-sc.astype(np.float64), kind="stable")
+            order = order[sc[order] > sthr]
+            sel = []
+            for i in order:
+                if len(sel) >= per_class:
+                    break
+                if sel and np.any(_nms_iou_vs(bx[i], bx[sel]) > thr):
+                    continue
+                sel.append(int(i))
+            cand.extend((float(sc[i]), c, pos, i) for pos, i in enumerate(sel))
+        cand.sort(key=lambda t: (-t[0], t[1], t[2]))
+        cand = cand[:min(out_n, total)]
+        nv[b] = len(cand)
+        for r, (_, c, _, i) in enumerate(cand):
+            kept = boxes[b, i, c if q > 1 else 0, :]
+            nb[b, r] = np.clip(kept, F32(0), F32(1)) if clip_boxes else kept
+            ns[b, r] = scores[b, i, c]
+            nc[b, r] = F32(c)
+            ni[b, r] = i
     if return_indices:
         return nb, ns, nc, nv, ni
     return nb, ns, nc, nv

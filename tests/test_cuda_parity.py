@@ -950,3 +950,21 @@ def test_proposals_with_regenerated_anchors_equal_anchor_tensor(T, cfg, B):
     b = T.tfrpn.generate_proposals(T.cu(reg), T.cu(cls), None, hp, pre_nms_topn=6000)
     for x, y in zip(a, b):
         assert T.torch.equal(x, y)
+
+
+# ---------------------------------------------------------------- multi-class NMS (utils/bbox_utils.py:53-55 allows total_labels > 1)
+@pytest.mark.parametrize("K,C,q,per_class,total,pad,sthr", [(200, 3, 1, 20, 30, False, float("-inf")), (300, 4, 4, 10, 100, True, 0.2),
+                                                            (64, 2, 1, 5, 7, True, 0.5), (500, 5, 5, 50, 40, False, 0.1)])
+def test_nms_multi_class_vs_oracle(T, K, C, q, per_class, total, pad, sthr):
+    rng = np.random.default_rng(K + C)
+    B = 3
+    ctr = rng.uniform(0.1, 0.9, size=(B, K, q, 2)); sz = rng.uniform(0.05, 0.4, size=(B, K, q, 2))
+    boxes = np.clip(np.concatenate([ctr - sz / 2, ctr + sz / 2], -1), 0, 1).astype(F32)
+    scores = rng.uniform(0, 1, size=(B, K, C)).astype(F32)
+    scores[0, :5, :] = 0.75                       # equal scores inside a class and across classes
+    kw = dict(max_output_size_per_class=per_class, max_total_size=total, iou_threshold=0.5, score_threshold=sthr,
+              pad_per_class=pad)
+    got = [T.np(x) for x in T.bbox.non_max_suppression(T.cu(boxes), T.cu(scores), return_indices=True, **kw)]
+    want = O.combined_non_max_suppression(boxes, scores, return_indices=True, **kw)
+    assert np.array_equal(got[3], want[3]) and np.array_equal(got[4], want[4])
+    assert bits_equal(got[0], want[0]) and bits_equal(got[1], want[1]) and bits_equal(got[2], want[2])
