@@ -507,8 +507,8 @@ def test_rejects_bad_inputs(T):
     with pytest.raises(ValueError):
         T.train.calculate_rpn_actual_outputs(anchors[:100], T.cu(np.zeros((1, 2, 4), F32)),
                                              T.cu(np.zeros((1, 2), np.int32)), hp)
-    with pytest.raises(NotImplementedError):
-        T.bbox.non_max_suppression(T.cu(np.zeros((1, 4, 2, 4), F32)), T.cu(np.zeros((1, 4, 2), F32)),
+    with pytest.raises(ValueError):    # q must be 1 or the number of classes (TF raises too)
+        T.bbox.non_max_suppression(T.cu(np.zeros((1, 4, 2, 4), F32)), T.cu(np.zeros((1, 4, 3), F32)),
                                    max_output_size_per_class=2, max_total_size=2)
     with pytest.raises(ValueError):
         T.bbox.top_k_boxes(T.cu(np.zeros((1, 4), F32)), 5)

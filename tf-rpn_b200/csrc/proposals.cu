@@ -182,6 +182,33 @@ __device__ __forceinline__ bool nms_suppresses_fast(float4 ci, float ai, float4 
 }
 #define TFRPN_FAR_BOX make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f)
 
+// Cheap conservative pre-test for SANITISED boxes and t.fast: `false` means IoU is certainly not > thr, so the pair
+// test above is only evaluated for the few pairs that pass (a candidate meets at most a handful of boxes it really
+// overlaps that much).  IoU = inter / (S - inter) > thr  <=>  inter > thr / (1 + thr) * S with S = ai + aj; lo_s
+// carries a 2^-10 margin, three orders of magnitude above the rounding of either side, so no true suppression can
+// fail it.  Only the height is clamped at 0: a negative width makes the product <= 0 (or NaN for the far-away empty
+// box: -inf * 0), which fails `>=` as well.  11 instructions instead of 19 -- and 17 for two kept boxes in the packed
+// form (FADD2 / FMUL2; the min / max have no packed form).
+__device__ __forceinline__ bool nms_maybe(float4 ci, float ai, float4 cj, float aj, float lo_s) {
+    const float h = fmaxf(__fsub_rn(fminf(ci.z, cj.z), fmaxf(ci.x, cj.x)), 0.0f);
+    const float w = __fsub_rn(fminf(ci.w, cj.w), fmaxf(ci.y, cj.y));
+    return __fmul_rn(h, w) >= __fmul_rn(lo_s, __fadd_rn(ai, aj));
+}
+// bit 0: box k0 may suppress / be suppressed by c, bit 1: box k1
+__device__ __forceinline__ unsigned nms_maybe2(float4 c, f32x2 ca2, float4 k0, float a0, float4 k1, float a1, f32x2 lo2) {
+    const f32x2 y_top = pack2(fmaxf(c.x, k0.x), fmaxf(c.x, k1.x)), y_bot = pack2(fminf(c.z, k0.z), fminf(c.z, k1.z));
+    const f32x2 x_top = pack2(fmaxf(c.y, k0.y), fmaxf(c.y, k1.y)), x_bot = pack2(fminf(c.w, k0.w), fminf(c.w, k1.w));
+    float h0, h1, i0, i1, b0, b1;
+    unpack2(sub2(y_bot, y_top), h0, h1);
+    unpack2(mul2(pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f)), sub2(x_bot, x_top)), i0, i1);
+    unpack2(mul2(lo2, add2(ca2, pack2(a0, a1))), b0, b1);
+    return (i0 >= b0 ? 1u : 0u) | (i1 >= b1 ? 2u : 0u);
+}
+// the exact decision behind the pre-test
+__device__ __forceinline__ bool nms_suppresses_filtered(float4 ci, float ai, float4 cj, float aj, const IouThreshold& t) {
+    return nms_maybe(ci, ai, cj, aj, t.lo_s) && nms_suppresses_fast(ci, ai, cj, aj, t);
+}
+
 // descending bitonic sort of PR_THREADS composites, one per thread; thread t ends with rank t.
 // Strides < 32 use shuffles; strides >= 32 go through a double-buffered shared array (1 barrier each).
 __device__ __forceinline__ unsigned long long bitonic_sort_desc(unsigned long long v, unsigned long long* buf) {
@@ -403,12 +430,15 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                     bool dead = false;
                     if (thr.fast) {
                         int j = part;
+                        const f32x2 ca2 = pack2(ca, ca), lo2 = pack2(thr.lo_s, thr.lo_s);
                         for (; j + NMS_PARTS < nkept && !dead; j += 2 * NMS_PARTS) {
-                            const bool d0 = nms_suppresses_fast(cb, ca, kbox[j], karea[j], thr);
-                            const bool d1 = nms_suppresses_fast(cb, ca, kbox[j + NMS_PARTS], karea[j + NMS_PARTS], thr);
-                            dead = d0 || d1;
+                            const unsigned m = nms_maybe2(cb, ca2, kbox[j], karea[j], kbox[j + NMS_PARTS], karea[j + NMS_PARTS], lo2);
+                            if (m != 0u) {   // rare: the exact test for the pairs that passed
+                                if (m & 1u) dead = nms_suppresses_fast(cb, ca, kbox[j], karea[j], thr);
+                                if (!dead && (m & 2u)) dead = nms_suppresses_fast(cb, ca, kbox[j + NMS_PARTS], karea[j + NMS_PARTS], thr);
+                            }
                         }
-                        if (!dead && j < nkept) dead = nms_suppresses_fast(cb, ca, kbox[j], karea[j], thr);
+                        if (!dead && j < nkept) dead = nms_suppresses_filtered(cb, ca, kbox[j], karea[j], thr);
                     } else {
                         for (int j = part; j < nkept && !dead; j += NMS_PARTS) dead = nms_suppresses(cb, ca, kbox[j], karea[j], thr);
                     }
@@ -441,7 +471,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) proposal_kernel(PropParams p) {
                 for (int e = sub; e < len; e += 16) {
                     const int i = slot[e < iA ? iA : iB];
                     const int j = slot[e < iA ? e : e - iA];
-                    if (thr.fast ? nms_suppresses_fast(cbox[j], carea[j], cbox[i], carea[i], thr)
+                    if (thr.fast ? nms_suppresses_filtered(cbox[j], carea[j], cbox[i], carea[i], thr)
                                  : nms_suppresses(cbox[j], carea[j], cbox[i], carea[i], thr))
                         atomicOr(&mask32[i * 4 + (j >> 5)], 1u << (j & 31));
                 }
@@ -610,14 +640,18 @@ __device__ __forceinline__ bool kept_list_suppresses(float4 cb, float ca, const 
     bool dead = false;
     int j = first;
     if (thr.fast) {
+        const f32x2 ca2 = pack2(ca, ca), lo2 = pack2(thr.lo_s, thr.lo_s);
         for (; j + 3 * stride < nkept && !dead; j += 4 * stride) {
-            const bool d0 = nms_suppresses_fast(cb, ca, kbox[j], karea[j], thr);
-            const bool d1 = nms_suppresses_fast(cb, ca, kbox[j + stride], karea[j + stride], thr);
-            const bool d2 = nms_suppresses_fast(cb, ca, kbox[j + 2 * stride], karea[j + 2 * stride], thr);
-            const bool d3 = nms_suppresses_fast(cb, ca, kbox[j + 3 * stride], karea[j + 3 * stride], thr);
-            dead = (d0 || d1) || (d2 || d3);
+            const unsigned m = nms_maybe2(cb, ca2, kbox[j], karea[j], kbox[j + stride], karea[j + stride], lo2) |
+                               (nms_maybe2(cb, ca2, kbox[j + 2 * stride], karea[j + 2 * stride], kbox[j + 3 * stride],
+                                           karea[j + 3 * stride], lo2) << 2);
+            if (m != 0u) {   // rare: the exact test for the pairs that passed
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (!dead && ((m >> u) & 1u)) dead = nms_suppresses_fast(cb, ca, kbox[j + u * stride], karea[j + u * stride], thr);
+            }
         }
-        for (; j < nkept && !dead; j += stride) dead = nms_suppresses_fast(cb, ca, kbox[j], karea[j], thr);
+        for (; j < nkept && !dead; j += stride) dead = nms_suppresses_filtered(cb, ca, kbox[j], karea[j], thr);
     } else {
         for (; j < nkept && !dead; j += stride) dead = nms_suppresses(cb, ca, kbox[j], karea[j], thr);
     }
@@ -969,7 +1003,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T, (T <= 512 && CL 
                 auto pair = [&](int e, int& i, int& j) -> bool {
                     i = e < iA ? iA : iB;
                     j = e < iA ? e : e - iA;
-                    return thr.fast ? nms_suppresses_fast(cbox_all[pos + j], carea_all[pos + j], cbox_all[pos + i], carea_all[pos + i], thr)
+                    return thr.fast ? nms_suppresses_filtered(cbox_all[pos + j], carea_all[pos + j], cbox_all[pos + i], carea_all[pos + i], thr)
                                     : nms_suppresses(cbox_all[pos + j], carea_all[pos + j], cbox_all[pos + i], carea_all[pos + i], thr);
                 };
                 int e = sub;
@@ -1174,12 +1208,19 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(const __grid_con
         unsigned int word = 0u;
         if (thr.fast) {
             if (jmax == 32) {
+                const f32x2 ai2 = pack2(ai, ai), lo2 = pack2(thr.lo_s, thr.lo_s);
+                unsigned int cand = 0u;              // pairs that pass the cheap pre-test ...
 #pragma unroll 8
-                for (int jj = 0; jj < 32; ++jj)
+                for (int jj = 0; jj < 32; jj += 2)
+                    cand |= nms_maybe2(ci, ai2, jbox[jj], jarea[jj], jbox[jj + 1], jarea[jj + 1], lo2) << jj;
+                while (cand != 0u) {                 // ... get the exact test (a handful per row)
+                    const int jj = __ffs(cand) - 1;
+                    cand &= cand - 1u;
                     word |= nms_suppresses_fast(jbox[jj], jarea[jj], ci, ai, thr) ? (1u << jj) : 0u;
+                }
             } else {
                 for (int jj = 0; jj < jmax; ++jj)
-                    word |= nms_suppresses_fast(jbox[jj], jarea[jj], ci, ai, thr) ? (1u << jj) : 0u;
+                    word |= nms_suppresses_filtered(jbox[jj], jarea[jj], ci, ai, thr) ? (1u << jj) : 0u;
             }
         } else {
             for (int jj = 0; jj < jmax; ++jj)
@@ -1353,6 +1394,7 @@ static IouThreshold make_threshold(float thr) {
     t.mid = ((double)thr + (double)nxt) * 0.5;   // exact: 25 significant bits
     t.lo_f = (float)((double)thr * (1.0 - 1.0 / 4096.0));
     t.hi_f = (float)((double)thr * (1.0 + 1.0 / 4096.0));
+    t.lo_s = (float)((double)thr / (1.0 + (double)thr) * (1.0 - 1.0 / 1024.0));
     uint32_t nb;
     memcpy(&nb, &nxt, 4);
     t.tie_up = ((nb & 1u) == 0u) ? 1 : 0;        // a tie rounds to the even mantissa
