@@ -729,7 +729,9 @@ def e2e_rpn(args, wl, lib, _lib, h, hp, anchors, np_sets, tcfg, pcfg, wall, worl
             tickets.append(t)
         pipe.drain()
 
-    Ke = min(K, 400)
+    # e2e is wall-clock over a pipeline DEPTH steps deep: a 20-step run would mostly measure its fill and drain, so the
+    # loop is at least 200 steps long whatever --steps says (the count is reported as e2e.steps)
+    Ke = min(max(K, 200), 400)
     pipelined(2 * DEPTH)
     t_e2e = wall(pipelined, Ke)
     h2d_pipe, d2h_pipe = pipe.last_copy_bytes()

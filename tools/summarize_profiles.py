@@ -65,15 +65,18 @@ for r in data:
     us = float(r[di]) * {"us": 1.0, "ns": 1e-3, "ms": 1e3}.get(U[di], 1.0)
     # launches of one shape can still be different modes (top-k of 10 vs of 6000): half-octave duration buckets
     grp = "grid=%s smem=%s%s ~%dus" % (r[gi], r[si], U[si], round(2 ** (round(math.log2(max(us, 0.5)) * 2) / 2)))
-    g = acc.setdefault(name, collections.OrderedDict()).setdefault(grp, {"bytes": [], "us": []})
+    g = acc.setdefault(name, collections.OrderedDict()).setdefault(grp, {"bytes": [], "us": [], "inst": []})
     g["bytes"].append(float(r[ri]) * unit[U[ri]] + float(r[wi]) * unit[U[wi]])
     g["us"].append(us)
+    if "smsp__inst_executed.sum" in H:
+        g["inst"].append(float(r[H.index("smsp__inst_executed.sum")]))
 mean = lambda v: sum(v) / len(v)
 per_name, groups = collections.OrderedDict(), collections.OrderedDict()
 for name, gs in acc.items():
     best = max(gs.items(), key=lambda kv: mean(kv[1]["us"]))
     per_name[name] = round(mean(best[1]["bytes"]))
-    groups[name] = {k: {"dram_bytes": round(mean(v["bytes"])), "avg_us": round(mean(v["us"]), 2), "launches": len(v["us"])}
+    groups[name] = {k: dict({"dram_bytes": round(mean(v["bytes"])), "avg_us": round(mean(v["us"]), 2), "launches": len(v["us"])},
+                            **({"warp_instr": round(mean(v["inst"]))} if v["inst"] else {}))
                     for k, v in gs.items()}
 with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
     json.dump({"source": "profiles/%s_kernels.csv (ncu --set full --clock-control none, per launch)" % tag,
