@@ -110,6 +110,38 @@ def test_expand_targets_host_matches_numpy_scatter():
     assert lib.tfrpn_expand_targets_host(None, None, 1, 1, 1, None, 0, None) == -1
 
 
+def test_expand_labels_host_matches_numpy():
+    """tfrpn_expand_labels_host (the host side of tfrpn_rpn_targets_sparse): codes 2 * anchor + label -> dense labels,
+    from scratch (every other entry -1) and incrementally (only the previous step's entries are reset)"""
+    import numpy as np
+    from tfrpn import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    B, N, Q = 3, 500, 40
+    def codes_for(seed):
+        r = np.random.default_rng(seed)
+        c = np.full((B, Q), -1, np.int32)
+        for b in range(B):
+            n = int(r.integers(0, Q + 1))
+            idx = r.choice(N, size=n, replace=False)
+            c[b, :n] = 2 * idx + r.integers(0, 2, size=n)
+        return c
+    def dense(c):
+        out = np.full((B, N), -1.0, np.float32)
+        for b in range(B):
+            for v in c[b][c[b] >= 0]:
+                out[b, v >> 1] = float(v & 1)
+        return out
+    c1, c2 = codes_for(1), codes_for(2)
+    labels = rng.normal(size=(B, N)).astype(np.float32)          # garbage: a full rebuild must not depend on it
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert lib.tfrpn_expand_labels_host(vp(c1), B, N, Q, None, 0, vp(labels)) == 0
+    assert np.array_equal(labels, dense(c1))
+    assert lib.tfrpn_expand_labels_host(vp(c2), B, N, Q, vp(c1), Q, vp(labels)) == 0
+    assert np.array_equal(labels, dense(c2))
+    assert lib.tfrpn_expand_labels_host(None, B, N, Q, None, 0, vp(labels)) != 0
+
+
 def test_ctypes_structs_match_header_layout(tmp_path):
     """Every struct that crosses the C ABI: size and field offsets of the ctypes mirror (tfrpn/_lib.py) equal
     what a C compiler makes of include/tfrpn.h (the header is plain C: gcc compiles it without CUDA)."""

@@ -32,7 +32,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import rpn_oracle as O
     from tfrpn import synthetic
-    from tfrpn.sharding import gather_rows, shard, shard_bounds
+    from tfrpn.sharding import gather_equal, gather_rows, shard, shard_bounds
     hp = O.get_hyper_params("vgg16")
     anchors = O.generate_anchors(hp)
     B = 5                                        # ragged split: 3 + 2
@@ -44,6 +44,8 @@ def _worker(rank, world, port, q):
     d, l = O.calculate_rpn_actual_outputs(anchors, my_b.numpy(), my_l.numpy(), hp, seed=3, offset=2, image_offset=off)
     full_l = gather_rows(torch.from_numpy(l.reshape(hi - lo, -1)), B)
     full_d = gather_rows(torch.from_numpy(d), B)
+    eq = gather_equal(torch.full((2, 3), float(rank)))          # equal blocks: one all_gather_into_tensor
+    assert eq.shape == (2 * world, 3) and all(bool((eq[2 * r:2 * r + 2] == r).all()) for r in range(world))
     if rank == 0:
         rd, rl = O.calculate_rpn_actual_outputs(anchors, gtb, gtl, hp, seed=3, offset=2)
         q.put(bool(np.array_equal(full_l.numpy(), rl.reshape(B, -1)) and np.array_equal(full_d.numpy(), rd)))
