@@ -68,7 +68,10 @@ def rand_boxes(rng, *shape):
                                            (2, 8649, 50, False), (2, 1000, 300, False), (5, 129, 3, True),
                                            # G % 4 == 0 / G % 2 == 0: 4 / 2 GT columns per thread (16- / 8-byte stores)
                                            (2, 300, 200, True), (2, 513, 52, False), (3, 100, 6, True),
-                                           (1, 40, 1024, False), (1, 33, 600, False), (1, 20, 1026, False)])
+                                           (1, 40, 1024, False), (1, 33, 600, False), (1, 20, 1026, False),
+                                           # G % 4 == 2: 16-byte stores over row pairs; odd N*G/2 shifts every other image by 8 bytes
+                                           (3, 8649, 50, False), (4, 301, 6, True), (5, 257, 2, True), (3, 1000, 10, False),
+                                           (2, 255, 510, False), (3, 511, 50, True), (2, 256, 50, False)])
 def test_iou_map_bit_exact(T, B, N, G, batched):
     rng = np.random.default_rng(B * 1000 + N + G)
     boxes = rand_boxes(rng, B, N) if batched else rand_boxes(rng, N)
