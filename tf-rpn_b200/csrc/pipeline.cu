@@ -2,32 +2,32 @@
 //
 // This is the call site the reference drives from Keras' generator thread (utils/train_utils.py:67-82,
 // trainer.py:48-49,64-69): every step a padded host batch goes in and (bbox_deltas, bbox_labels) come
-// out; predictor.py:48-60 does the same with the head outputs.  A step moves ~11 MB each way at C2
-// while its kernels take ~0.1 ms, so the step is PCIe-bound and the job of this file is to keep BOTH
-// directions of the link busy:
+// out; predictor.py:48-60 does the same with the head outputs.  Dense, a C2 step would move ~11 MB each way
+// while its kernels take ~0.05 ms, so this file (a) keeps several steps in flight and (b) moves fewer bytes.
 //
-//   stream in   : H2D gt (tiny), then rpn_reg / rpn_cls chunk by chunk
-//   stream tgt  : target kernels of chunk c            (needs gt)
-//   stream prop : proposal kernel of chunk c           (needs its reg/cls chunk)
-//   stream out  : D2H deltas/labels of chunk c as soon as its kernels are done, then the small
-//                 proposal results
+// (a) Each in-flight step owns a SLOT: device + page-locked staging, its own copy-in / proposal / copy-out
+//     streams, events.  The target kernels of all slots share one stream (they share the handle's workspace).
+//     Results are bit-identical to the separate calls: images are independent and the counter RNG is keyed by
+//     the global image index.  A depth-1 pipeline is the synchronous step (tfrpn_rpn_step_host): chunked over
+//     images so that its own copies overlap its kernels, dense in both directions.
 //
-// Each in-flight step owns a SLOT (device + pinned staging, its own copy / proposal streams, events), so
-// with depth >= 2 the H2D of step i+1 runs under the D2H of step i: the steady-state cost of a step is
-// max(H2D, D2H, kernels) instead of their sum.  (The target kernels of all slots share one stream: they
-// share the handle's workspace.)  Results are bit-identical to the separate calls: images are independent
-// and the counter RNG is keyed by the global image index.
+// (b) Measured at C2 (profiles/r2d_*, r2_scale/): 11.1 MB in / 11.5 MB out -> 3.6 / 3.1 MB per step.
+//   two-phase proposals   rpn_reg is 80 % of the input bytes and NMS decodes ~560 of its 8649 rows per image.
+//                         Only the scores are copied; a rank launch returns the entry index of the first ranks;
+//                         the rows of the first `gather_rows` ranks are gathered ON THE HOST from the caller's
+//                         tensor -- page-locked or pageable, read in place -- into a compact block that follows
+//                         in one copy; the NMS launch reads rows by rank.  SM-issued loads of single rows over
+//                         PCIe run at ~0.4-0.6 G rows/s (tools/src/pcie_rows.cu, pcie_gather.cu): as slow as
+//                         copying the whole tensor, which is why the host gathers when it has the cores
+//                         (gather_rows_kernel is the device-side variant for hosts that have not).
+//   compact bbox_deltas   exactly zero outside the <= total_pos sampled positives (train_utils.py:137): only those
+//                         rows come back and host threads scatter them into the dense array when the step is
+//                         retired (optionally bbox_labels too, as codes of its entries != -1).
 //
-// Two things keep the BYTES down (measured at C2, profiles/r2d_*: 11.1 MB in / 11.5 MB out -> 3.1 / 2.9 MB):
-//   two-phase proposals   rpn_reg is 80 % of the input bytes and NMS decodes ~550 of its 8649 rows per
-//                         image.  Only the scores are copied; a rank launch returns the entry index of
-//                         the first ranks; a host function (cudaLaunchHostFunc, the library's worker
-//                         pool) gathers those rows from the caller's tensor -- pinned or pageable -- into
-//                         a compact block; the NMS launch reads rows by rank.  SM-issued loads of single
-//                         rows over PCIe run at ~0.4 G rows/s (tools/src/pcie_rows.cu): as slow as copying
-//                         the whole tensor, which is why the host gathers.
-//   compact bbox_deltas   exactly zero outside the <= total_pos sampled positives (train_utils.py:137):
-//                         only those rows come back and a host function scatters them into the dense array.
+// Host stages run on a SERVICE THREAD (polls the rank-copy events, gathers, enqueues the tail of the step) and a
+// WORKER POOL (gather, scatter, staging copies): cudaLaunchHostFunc costs ~150 us of stream time per call on this
+// box and serialises across streams (tools/src/hostfunc_lat.cu).  Device time stamps of every stage:
+// TFRPN_PIPE_TRACE=1 + tfrpn_pipeline_trace (tools/pipe_trace.py).
 #include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
