@@ -16,6 +16,15 @@
 //   4 top-k outputs, or greedy NMS rounds of 128 candidates: test against the kept list, build
 //     predecessor masks inside the round, resolve them in one warp with ballots.
 //   In the fused mode boxes are decoded (+clipped) on the fly, for the examined candidates only.
+//
+// Kernels of this file:
+//   proposal_kernel                one 1024-thread CTA per image (the default above 8 images per launch)
+//   proposal_cluster_kernel<CL,T>  the same algorithm on a thread-block cluster per image (<= 8 images per launch;
+//                                  also MODE_RANK / presorted launches of the host pipeline's two-phase transfer)
+//   nms_mask_kernel, nms_sweep_kernel   matrix NMS over the ranks of a MODE_RANK launch (opt-in, TFRPN_NMS_PATH=matrix)
+//   gather_rows_kernel             candidate rows of a page-locked host tensor -> compact device array (pipeline.cu)
+//   pre_hist / pre_count / pre_scatter_kernel   large-N prefilter (N >= 40 000)
+// The NMS pair test runs behind a cheap conservative pre-test (nms_maybe / nms_maybe2): see there.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
