@@ -736,6 +736,7 @@ def e2e_rpn(args, wl, lib, _lib, h, hp, anchors, np_sets, tcfg, pcfg, wall, worl
     t_e2e = wall(pipelined, Ke)
     h2d_pipe, d2h_pipe = pipe.last_copy_bytes()
     t_fill = wall(lambda n: pipelined(n, True), Ke)
+    pipe.set_stable_outputs(True)   # the ring `outs` is written by the pipeline only: no per-step memset of the dense deltas
     pageable(2 * DEPTH)
     t_page = wall(pageable, Ke)
     h2d_page, d2h_page = pipe.last_copy_bytes()
@@ -758,7 +759,8 @@ def e2e_rpn(args, wl, lib, _lib, h, hp, anchors, np_sets, tcfg, pcfg, wall, worl
             "pageable_arrays": {"value": world * B * Ke / t_page, "ms_per_step": 1e3 * t_page / Ke,
                                 "h2d_bytes_per_step": h2d_page, "d2h_bytes_per_step": d2h_page,
                                 "api": "HostPipeline.submit_arrays (tfrpn_pipeline_submit): the producer's pageable NumPy "
-                                       "arrays in, pageable dense arrays out, no copy by the caller"},
+                                       "arrays in, a ring of pageable dense arrays out (TFRPN_PIPE_OPT_STABLE_OUTPUTS), no copy "
+                                       "by the caller"},
             "with_producer_fill": {"value": world * B * Ke / t_fill, "ms_per_step": 1e3 * t_fill / Ke,
                                    "note": "the same loop with the producer's pageable NumPy batch copied into the slot's "
                                            "pinned block inside every step (single-threaded memcpy)"},

@@ -321,6 +321,13 @@ TFRPN_API int tfrpn_pipeline_submit_acquired(tfrpn_pipeline p, const float* anch
                                    const tfrpn_target_cfg* tcfg_or_null, const tfrpn_proposal_cfg* pcfg_or_null,
                                    int64_t* ticket_out);
 TFRPN_API int tfrpn_pipeline_wait(tfrpn_pipeline p, int64_t ticket);
+/* Options (set while no step is in flight; steps in flight are retired first).
+ * TFRPN_PIPE_OPT_STABLE_OUTPUTS = 1: the caller promises that every bbox_deltas array it passes to
+ * tfrpn_pipeline_submit is written by this pipeline only (the usual ring of output arrays).  An array the pipeline has
+ * filled before then still holds zeros plus the rows of that step, so only those rows are reset instead of zeroing
+ * 16 * B * N bytes per step.  Off by default: without the promise a stale array would keep foreign rows. */
+enum { TFRPN_PIPE_OPT_STABLE_OUTPUTS = 1 };
+TFRPN_API int tfrpn_pipeline_set_option(tfrpn_pipeline p, int option, int value);
 /* bytes the last submitted acquired step copies in each direction (bbox_deltas travels in compact form,
  * see tfrpn_rpn_targets_compact, and is expanded into the slot's dense host array by wait()) */
 TFRPN_API int tfrpn_pipeline_last_copy_bytes(tfrpn_pipeline p, int64_t* h2d_bytes, int64_t* d2h_bytes);

@@ -200,3 +200,35 @@ def test_submit_caller_buffers_two_phase(cuda_device, gather_rows, pinned):
         lib.tfrpn_destroy(h)
         for p in ptrs:
             lib.tfrpn_host_free(p)
+
+
+def test_submit_arrays_stable_outputs_ring(cuda_device):
+    """HostPipeline.submit_arrays on a ring of pageable output dicts with TFRPN_PIPE_OPT_STABLE_OUTPUTS: the dense
+    bbox_deltas of every step equals the oracle although only the previously written rows are reset"""
+    from tfrpn import HostPipeline, synthetic
+    hp = dict(O.get_hyper_params("vgg16"))
+    anchors_np = O.generate_anchors(hp)
+    B, G, depth = 6, 9, 3
+    pipe = HostPipeline(hp, depth=depth, device=cuda_device, pre_nms_topn=6000)
+    pipe.set_stable_outputs(True)
+    outs = [dict() for _ in range(depth)]
+    pending = []
+    try:
+        def check(item):
+            t, i, out, gtb, gtl, reg, cls = item
+            pipe.wait(t)
+            od, ol, wb, ws, wv, wk = want_for(anchors_np, hp, gtb, gtl, reg, cls, 4, i, 0)
+            assert bits_equal(out["bbox_labels"], ol) and close(out["bbox_deltas"], od)
+            assert np.array_equal(out["bbox_deltas"] != 0, od != 0)
+            assert np.array_equal(out["valid"], wv) and np.array_equal(out["keep_idx"], wk)
+        for i in range(8):
+            gtb, gtl = synthetic.gt_batch(np.random.default_rng(40 + i), B, G)
+            reg, cls = synthetic.head_outputs(np.random.default_rng(60 + i), B, 31, 31, 9)
+            if len(pending) == depth - 1:
+                check(pending.pop(0))
+            t, out = pipe.submit_arrays(gtb, gtl, reg, cls, out=outs[i % depth], seed=4, offset=i)
+            pending.append((t, i, out, gtb, gtl, reg, cls))
+        while pending:
+            check(pending.pop(0))
+    finally:
+        pipe.close()

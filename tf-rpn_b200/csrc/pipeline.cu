@@ -273,6 +273,11 @@ struct tfrpn_pipe {
     bool acq_live = false;
     long long last_h2d = 0, last_d2h = 0;             // bytes copied by the last submitted step
     long long last_pulled = 0;                        // bytes of rpn_reg rows gathered / pulled for the last RETIRED step
+    // TFRPN_PIPE_OPT_STABLE_OUTPUTS: the caller promises that the bbox_deltas arrays it passes to submit() are written by
+    // this pipeline only, so an array seen before still holds zeros plus the rows of its last step (no 4*B*N*4-byte memset)
+    bool stable_outputs = false;
+    struct CallerDense { float* ptr; int B, N, TP; std::vector<int32_t> idx; };
+    std::vector<CallerDense> caller_dense;            // most recent first, at most 64 arrays
     int gather_rows = 640;                            // rows of rpn_reg per image the two-phase transfer sends (adapts)
     bool gather_adapt = true;
     bool device_gather = false;                       // page-locked tensors: gather on the device instead of the host
@@ -373,11 +378,18 @@ static void expand_targets(tfrpn_pipe* p, Slot& s, float* labels_dst) {
     const int32_t* prev = reuse ? s.prev_idx.data() : nullptr;
     const int32_t* prev_l = reuse ? s.prev_lbl.data() : nullptr;
     float* dense = st.dense_dst;
+    int prev_tp = pTP;
+    tfrpn_pipe::CallerDense* known = nullptr;
+    if (!own && p->stable_outputs) {   // a caller's array this pipeline filled before: reset only the rows it wrote then
+        for (auto& cd : p->caller_dense)
+            if (cd.ptr == dense && cd.B == B && cd.N == N) { known = &cd; break; }
+        if (known) { prev = known->idx.data(); prev_tp = known->TP; }
+    }
     constexpr int PIECE = 2;        // images per chunk
     p->pool->run((B + PIECE - 1) / PIECE, [&](int c) {
         const int b0 = c * PIECE, nb = (B - b0 < PIECE) ? B - b0 : PIECE;
         tfrpn_expand_targets_host(idx + (size_t)b0 * TP, rows + (size_t)b0 * TP * 4, nb, N, TP,
-                                  prev ? prev + (size_t)b0 * pTP : nullptr, pTP, dense + (size_t)b0 * N * 4);
+                                  prev ? prev + (size_t)b0 * prev_tp : nullptr, prev_tp, dense + (size_t)b0 * N * 4);
         if (st.sparse_labels)
             tfrpn_expand_labels_host(codes + (size_t)b0 * Q, nb, N, Q, prev_l ? prev_l + (size_t)b0 * pQ : nullptr, pQ,
                                      labels_dst + (size_t)b0 * N);
@@ -387,6 +399,14 @@ static void expand_targets(tfrpn_pipe* p, Slot& s, float* labels_dst) {
         s.prev_lbl.assign(codes, codes + (size_t)B * Q);
         s.pB = B; s.pN = N; s.pTP = TP; s.pQ = Q; s.p_off_d = st.L.d;
         s.dense_clean = true;
+    } else if (p->stable_outputs) {
+        if (known) {
+            known->TP = TP;
+            known->idx.assign(idx, idx + (size_t)B * TP);
+        } else {
+            if (p->caller_dense.size() >= 64) p->caller_dense.pop_back();
+            p->caller_dense.insert(p->caller_dense.begin(), tfrpn_pipe::CallerDense{dense, B, N, TP, std::vector<int32_t>(idx, idx + (size_t)B * TP)});
+        }
     }
 }
 
@@ -1016,6 +1036,18 @@ extern "C" int tfrpn_pipeline_trace(tfrpn_pipeline p, int64_t ticket, float* ms1
     ms10[8] = s.gather_ms;
     ms10[9] = s.expand_ms;
     return 0;
+}
+
+extern "C" int tfrpn_pipeline_set_option(tfrpn_pipeline p, int option, int value) {
+    if (!p) return fail(TFRPN_ERR_BAD_ARG, "pipeline_set_option: null pipeline");
+    if (option == TFRPN_PIPE_OPT_STABLE_OUTPUTS) {
+        TFRPN_ENTER(p->h);
+        for (int i = 0; i < p->depth; ++i) if (int rc = slot_finish(p, p->slots[i])) return rc;   // nothing in flight while it changes
+        p->stable_outputs = value != 0;
+        if (!p->stable_outputs) p->caller_dense.clear();
+        return 0;
+    }
+    return fail(TFRPN_ERR_BAD_ARG, "pipeline_set_option: unknown option %d", option);
 }
 
 extern "C" int tfrpn_pipeline_wait(tfrpn_pipeline p, int64_t ticket) {

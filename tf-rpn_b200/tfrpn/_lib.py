@@ -93,6 +93,7 @@ PROTOTYPES = {
     "tfrpn_pipeline_acquire": (I, [P, I, I, I, I, C.POINTER(StepBuffers)]),
     "tfrpn_pipeline_submit_acquired": (I, [P, P, C.POINTER(TargetCfg), C.POINTER(ProposalCfg), C.POINTER(C.c_int64)]),
     "tfrpn_pipeline_wait": (I, [P, C.c_int64]),
+    "tfrpn_pipeline_set_option": (I, [P, I, I]),
     "tfrpn_pipeline_last_copy_bytes": (I, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tfrpn_pipeline_trace": (I, [P, C.c_int64, C.POINTER(C.c_float)]),
     "tfrpn_pipeline_drain": (I, [P]),

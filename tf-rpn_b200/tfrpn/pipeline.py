@@ -121,6 +121,12 @@ class HostPipeline:
             _lib.check(rc)
         return self._ticket.value
 
+    def set_stable_outputs(self, on=True):
+        """Promise that the ``out`` arrays given to :meth:`submit_arrays` are written by this pipeline only (the usual
+        ring of ``depth`` output dicts).  The library then resets just the rows it wrote into an array the last time
+        instead of zeroing the whole dense ``bbox_deltas`` every step (TFRPN_PIPE_OPT_STABLE_OUTPUTS)."""
+        _lib.check(self._lib.tfrpn_pipeline_set_option(self._pipe, 1, int(bool(on))))
+
     def submit_arrays(self, gt_boxes=None, gt_labels=None, rpn_reg=None, rpn_cls=None, out=None, seed=None, offset=None,
                       image_offset=0):
         """One step on the caller's own host arrays (``tfrpn_pipeline_submit``): NumPy arrays as the reference's
