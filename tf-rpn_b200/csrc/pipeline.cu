@@ -791,6 +791,7 @@ static int pipe_submit(tfrpn_pipe* p, const StepArgs& a, bool acquired, bool ord
     st.device_gather = two_phase && st.reg_pinned && p->device_gather;
     s.pulled = two_phase && st.reg_pinned;
     s.gathered = 0;
+    s.gather_ms = s.expand_ms = 0.f;
     s.svc_rc = 0;
     s.svc_pending.store(two_phase && !st.device_gather ? 1 : 0, std::memory_order_release);
 
